@@ -1,0 +1,96 @@
+"""Shared helpers for the parity tests: golden fixtures and input resolution."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, os.path.join(ROOT, "sequence-alignment-gpu_b200"))
+import synth  # noqa: E402
+
+_seqs = None
+_mats = None
+_goldens = None
+
+
+def sequences():
+    global _seqs
+    if _seqs is None:
+        z = np.load(os.path.join(GOLD, "sequences.npz"))
+        _seqs = {k: z[k] for k in z.files}
+    return _seqs
+
+
+def matrices():
+    global _mats
+    if _mats is None:
+        _mats = {k: np.asarray(v, np.int32) for k, v in json.load(open(os.path.join(GOLD, "matrices.json"))).items()}
+    return _mats
+
+
+def goldens():
+    global _goldens
+    if _goldens is None:
+        _goldens = json.load(open(os.path.join(GOLD, "reference_goldens.json")))
+    return _goldens
+
+
+def sha(b: bytes) -> str:
+    return hashlib.sha256(b).hexdigest()
+
+
+def golden_inputs(g):
+    """-> (text, pattern, matrix) for a golden record (text is the longer)."""
+    if "text" in g:
+        t, p = np.asarray(g["text"], np.uint8), np.asarray(g["pattern"], np.uint8)
+    elif "files" in g:
+        a, b = (sequences()[f] for f in g["files"])
+        t, p = (a, b) if len(a) >= len(b) else (b, a)
+    elif "synth" in g:
+        s = g["synth"]
+        t, p = synth.synthetic_pair(s["n"], s["seed_base"], s["seed_mut"], protein=s["protein"])
+    else:
+        raise KeyError(g["name"])
+    mat = np.asarray(g["matrix_values"], np.int32) if "matrix_values" in g else matrices()[g["matrix"]]
+    assert len(t) == g["n"] and len(p) == g["m"], g["name"]
+    return t, p, mat
+
+
+def has_inputs(g):
+    if "files" in g:
+        return all(f in sequences() for f in g["files"])
+    return "text" in g or "synth" in g
+
+
+def check_against_golden(aln, g):
+    """aln: object with score/aln_len/start_text/start_pattern/aligned_text/aligned_pattern."""
+    r = g["ref"]
+    assert aln.score == r["score"], (g["name"], "score", aln.score, r["score"])
+    assert aln.aln_len == r["aln_len"], (g["name"], "aln_len", aln.aln_len, r["aln_len"])
+    assert aln.start_text == r["start_text"], (g["name"], "start_text", aln.start_text, r["start_text"])
+    assert aln.start_pattern == r["start_pattern"], (g["name"], "start_pattern")
+    assert sha(aln.aligned_text) == r["sha_text"], (g["name"], "aligned_text")
+    assert sha(aln.aligned_pattern) == r["sha_pattern"], (g["name"], "aligned_pattern")
+    for k, v in g.get("expect", {}).items():   # values copied from the reference's tests
+        got = getattr(aln, k)
+        got = got.decode() if isinstance(got, bytes) else got
+        assert got == v, (g["name"], k)
+
+
+def random_case(rng, alpha, n_max=200, m_max=None, similar=True):
+    """Random pair; similar=True makes the pattern a mutated copy (long paths, many ties)."""
+    n = int(rng.integers(1, n_max + 1))
+    t = rng.integers(0, alpha, n, dtype=np.uint8)
+    if similar:
+        p = synth.mutate_indices_numpy(t, rng, alpha)
+        if len(p) == 0:
+            p = t[:1].copy()
+    else:
+        m = int(rng.integers(1, (m_max or n) + 1))
+        p = rng.integers(0, alpha, m, dtype=np.uint8)
+    if len(p) > len(t):
+        t, p = p, t
+    return t, p

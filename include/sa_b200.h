@@ -1,0 +1,173 @@
+/*
+ * sa_b200.h -- C ABI of the B200-native pairwise alignment hot path.
+ *
+ * This is the drop-in boundary for the `-g` device path of
+ * robertszafa/sequence-alignment-gpu: every entry point below replaces a piece
+ * of /root/reference/alignSequenceGPU.cu (cited per function).  Plain pointers
+ * and sizes only; no C++/torch types.  The functions never print and never
+ * throw; they return SA_OK (0) or a negative sa_status.  There is NO CPU
+ * fallback: without a CUDA device every compute entry returns SA_ERR_NO_DEVICE.
+ *
+ * Conventions (identical to the reference's Request, SequenceAlignment.hpp:71-99):
+ *   - sequences are alphabet indices 0..alphabet_size-1, one per byte
+ *     (utilities.cpp:47-52), NOT ASCII;
+ *   - score_matrix is row-major with stride alphabet_size and is indexed
+ *     [pattern letter][text letter] (alignSequenceCPU.cpp:172,256);
+ *   - gap is a positive magnitude that is subtracted (linear gap penalty);
+ *   - alphabet has alphabet_size+1 chars, the last one is the gap char '-'
+ *     (SequenceAlignment.hpp:56-58);
+ *   - results are bit-identical to the reference's alignSequenceCPU
+ *     (alignSequenceCPU.cpp:287-333): score, numAlignmentBytes, both start
+ *     indices (incl. the 2^64-1 wrap for a zero-score local alignment) and
+ *     both aligned strings (forward order, no terminator).
+ */
+#ifndef SA_B200_H
+#define SA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SA_OK = 0,
+    SA_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
+    SA_ERR_MEMORY = -2,      /* device or pinned allocation failed (reference: MEM_ERROR, alignSequenceGPU.cu:541-546) */
+    SA_ERR_COPY = -3,        /* host<->device copy failed (reference: "could not copy from device memory", :588-594) */
+    SA_ERR_ARGUMENT = -4,    /* null pointer, empty sequence, residue >= alphabet_size, alphabet_size > 32 ... */
+    SA_ERR_SCORE_RANGE = -5, /* |score| or gap too large for the packed arithmetic (see DESIGN.md "ranges") */
+    SA_ERR_LAUNCH = -6,      /* kernel launch / execution error */
+    SA_ERR_CAPACITY = -7     /* caller-provided output buffer too small */
+} sa_status;
+
+enum { SA_GLOBAL = 0, SA_LOCAL = 1 };   /* programArgs::GLOBAL / LOCAL, SequenceAlignment.hpp:17 */
+
+/* Scoring scheme: the non-sequence half of Request (SequenceAlignment.hpp:87-91). */
+typedef struct {
+    int32_t        mode;           /* SA_GLOBAL (Needleman-Wunsch) or SA_LOCAL (Smith-Waterman) */
+    int32_t        alphabet_size;  /* 4 (DNA) or 23 (protein); any 2..32 is accepted */
+    const int32_t *score_matrix;   /* alphabet_size^2 ints, [pattern][text] */
+    int32_t        gap;            /* >= 0 */
+    const char    *alphabet;       /* alphabet_size+1 chars */
+} sa_scoring;
+
+/* One alignment result: Response (SequenceAlignment.hpp:101-120) as a POD. */
+typedef struct {
+    int32_t  score;
+    uint64_t aln_len;         /* numAlignmentBytes */
+    uint64_t start_text;      /* startInAlignedText */
+    uint64_t start_pattern;   /* startInAlignedPattern */
+} sa_result;
+
+/* Timing of the last call on a context, microseconds, from CUDA events on the
+ * context's stream.  Serves the reference's `#define BENCHMARK` behaviour
+ * (alignSequenceGPU.cu:555-558,613-626: return elapsed us of fill + D2H). */
+typedef struct {
+    double h2d_us;        /* host->device copies */
+    double fill_us;       /* DP fill kernels */
+    double traceback_us;  /* device traceback + string emission */
+    double d2h_us;        /* device->host copies of results */
+    double total_us;      /* first event to last event */
+    uint64_t cells;       /* sum over pairs of (pattern_len+1)*(text_len+1) (tests/benchmarks.cu:85) */
+    uint32_t kernel_launches;
+} sa_timing;
+
+typedef struct sa_context sa_context;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+
+/* Number of usable CUDA devices (0 when none). */
+int sa_device_count(void);
+
+/* Creates a context bound to `device` (the reference hard-codes device 0,
+ * alignSequenceGPU.cu:476).  Owns a stream, pinned staging and a growing
+ * device workspace, so repeated calls do not pay cudaMalloc/cudaMallocHost per
+ * call like initMemory does (alignSequenceGPU.cu:362-461). */
+int sa_create(int device, sa_context **out);
+void sa_destroy(sa_context *ctx);
+
+const char *sa_status_string(int status);
+int sa_last_timing(const sa_context *ctx, sa_timing *out);
+/* cudaError_t of the last failing CUDA call on this context (0 if none): the reference
+ * swallows these (no cudaGetLastError after launches, alignSequenceGPU.cu:575-611). */
+int sa_last_cuda_error(const sa_context *ctx);
+
+/* ---- single pair: replaces alignSequenceGPU (alignSequenceGPU.cu:463-653) ---
+ * HOST buffers in, HOST buffers out.  aligned_text / aligned_pattern must hold
+ * at least text_len + pattern_len bytes each (capacity given in out_capacity).
+ * Any pair size: short pairs go through the batch kernel, long ones through
+ * the persistent wavefront kernel with the direction matrix in HBM. */
+int sa_align(sa_context *ctx, const sa_scoring *scoring,
+             const uint8_t *text, uint64_t text_len,
+             const uint8_t *pattern, uint64_t pattern_len,
+             sa_result *result, char *aligned_text, char *aligned_pattern,
+             uint64_t out_capacity);
+
+/* Fill only, no traceback (what the reference times under BENCHMARK).  Returns
+ * the score (and for SA_LOCAL the row-major-first arg-max as i*(n+1)+j). */
+int sa_fill_only(sa_context *ctx, const sa_scoring *scoring,
+                 const uint8_t *text, uint64_t text_len,
+                 const uint8_t *pattern, uint64_t pattern_len,
+                 int32_t *score, uint64_t *argmax);
+
+/* DEVICE-resident single pair through the long-pair kernels: d_text / d_pattern hold the
+ * residues, d_aligned_* have capacity text_len+pattern_len and receive the strings
+ * right-aligned (they end at the buffer end), d_result4 receives
+ * {aln_len, start_text, start_pattern, score}.  Enqueued on `stream`, no synchronisation. */
+int sa_align_device(sa_context *ctx, const sa_scoring *scoring,
+                    const uint8_t *d_text, uint64_t text_len,
+                    const uint8_t *d_pattern, uint64_t pattern_len,
+                    char *d_aligned_text, char *d_aligned_pattern, uint64_t *d_result4,
+                    void *stream);
+
+/* ---- batch of independent pairs (new surface; the reference's "batch" is a
+ * loop of single calls, tests/benchmarks.cu:318-322) --------------------------
+ * CSR layout: pair p's text is text[text_off[p] .. text_off[p+1]) and likewise
+ * for pattern.  Aligned strings of pair p are written to
+ *   aligned_text   [aln_off[p] .. aln_off[p] + results[p].aln_len)
+ * where aln_off is an OUTPUT array of n_pairs entries and the two output
+ * arenas must hold text_off[n_pairs] + pattern_off[n_pairs] bytes each. */
+typedef struct {
+    uint64_t       n_pairs;
+    const uint8_t *text;         const int64_t *text_off;     /* n_pairs+1 */
+    const uint8_t *pattern;      const int64_t *pattern_off;  /* n_pairs+1 */
+} sa_batch;
+
+typedef struct {
+    sa_result *results;          /* n_pairs */
+    uint64_t  *aln_off;          /* n_pairs, offsets into the two arenas */
+    char      *aligned_text;     /* arena */
+    char      *aligned_pattern;  /* arena */
+    uint64_t   arena_capacity;   /* bytes available in each arena */
+} sa_batch_out;
+
+/* HOST buffers; copies in, aligns on the device, copies results out, pipelined
+ * in chunks over the context's streams. */
+int sa_align_batch(sa_context *ctx, const sa_scoring *scoring,
+                   const sa_batch *batch, sa_batch_out *out);
+
+/* DEVICE-resident variant: every pointer in `batch` and `out` is a device
+ * pointer (e.g. torch tensors' data_ptr()), work is enqueued on `stream`
+ * (a cudaStream_t; 0 = the context's own stream) and the call returns without
+ * synchronising.  max_text_len / max_pattern_len bound the pair sizes (they
+ * size the direction workspace). */
+int sa_align_batch_device(sa_context *ctx, const sa_scoring *scoring,
+                          const sa_batch *batch, sa_batch_out *out,
+                          uint32_t max_text_len, uint32_t max_pattern_len,
+                          void *stream);
+
+/* ---- multi-GPU helpers ------------------------------------------------------
+ * Deterministic cell-balanced split of a batch over `world` ranks (each rank
+ * aligns pairs [first[r], first[r+1]) ): no data-path collective is needed. */
+int sa_partition_batch(const int64_t *text_off, const int64_t *pattern_off,
+                       uint64_t n_pairs, int world, uint64_t *first /* world+1 */);
+
+/* Library / build info. */
+const char *sa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SA_B200_H */

@@ -134,6 +134,9 @@ class Reference:
                                     C.POINTER(C.c_int), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.c_void_p, C.c_void_p]
+        L.ref_align_cpu_batch.restype = C.c_int
+        L.ref_align_cpu_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_fill_cpu.restype = C.c_int
         L.ref_fill_cpu.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
@@ -170,6 +173,23 @@ class Reference:
             raise MemoryError("reference returned error")
         return Alignment(score.value, ln.value, st.value, sp.value,
                          outT[:ln.value].tobytes(), outP[:ln.value].tobytes())
+
+    def align_batch(self, mode, alpha, matrix, gap, text, text_off, pattern, pattern_off, nthreads=1):
+        """Scores and alignment lengths of a CSR batch on ``nthreads`` host threads."""
+        text, pattern = _u8(text), _u8(pattern)
+        toff = np.ascontiguousarray(text_off, dtype=np.int64)
+        poff = np.ascontiguousarray(pattern_off, dtype=np.int64)
+        full = np.zeros(23 * 23, np.int32)
+        full[:alpha * alpha] = _i32(matrix).ravel()[:alpha * alpha]
+        N = len(toff) - 1
+        scores = np.zeros(N, np.int32)
+        lens = np.zeros(N, np.uint64)
+        bad = self.lib.ref_align_cpu_batch(mode, alpha, full.ctypes.data, gap, text.ctypes.data, toff.ctypes.data,
+                                           pattern.ctypes.data, poff.ctypes.data, N, nthreads,
+                                           scores.ctypes.data, lens.ctypes.data)
+        if bad:
+            raise MemoryError(f"{bad} pairs failed in the reference")
+        return scores, lens
 
     def fill(self, mode, alpha, matrix, gap, text, pattern, M=None):
         text, pattern = _u8(text), _u8(pattern)

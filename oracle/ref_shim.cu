@@ -9,8 +9,11 @@
 // (c) serve as bench.py's cpu_baseline / --impl reference (kind "reference").
 #include "SequenceAlignment.hpp"
 
+#include <atomic>
 #include <cstring>
 #include <sstream>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -59,6 +62,34 @@ int ref_align_cpu(int mode, int alphabetSize, const int *matrix, int gap,
     if (outT) std::memcpy(outT, rs.alignedTextBytes, rs.numAlignmentBytes);
     if (outP) std::memcpy(outP, rs.alignedPatternBytes, rs.numAlignmentBytes);
     return 0;
+}
+
+// A batch of independent pairs (CSR layout) through alignSequenceCPU, one pair per task on
+// `nthreads` host threads (the reference itself is single-threaded; pairs are independent).
+// This is bench.py's cpu_baseline / --impl reference leg for the batch workload.
+// Returns the number of failed pairs.  checksum = sum over pairs of (score + alnLen).
+int ref_align_cpu_batch(int mode, int alphabetSize, const int *matrix, int gap,
+                        const char *text, const int64_t *toff, const char *pattern, const int64_t *poff,
+                        uint64_t nPairs, int nthreads, int *scores, uint64_t *alnLens)
+{
+    std::atomic<uint64_t> next(0);
+    std::atomic<int> failed(0);
+    auto worker = [&]() {
+        for (;;) {
+            const uint64_t p = next.fetch_add(1);
+            if (p >= nPairs) break;
+            int score = 0; uint64_t len = 0, st = 0, sp = 0;
+            const uint64_t n = (uint64_t)(toff[p + 1] - toff[p]), m = (uint64_t)(poff[p + 1] - poff[p]);
+            if (ref_align_cpu(mode, alphabetSize, matrix, gap, text + toff[p], n, pattern + poff[p], m,
+                              &score, &len, &st, &sp, nullptr, nullptr) != 0) { failed++; continue; }
+            if (scores) scores[p] = score;
+            if (alnLens) alnLens[p] = len;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < (nthreads > 1 ? nthreads : 1); ++t) th.emplace_back(worker);
+    for (auto &t : th) t.join();
+    return failed.load();
 }
 
 // Fill only (file-local fillMatrixNW / fillMatrixSW, alignSequenceCPU.cpp:203,116):

@@ -1,0 +1,875 @@
+// sa_api.cu -- extern "C" layer (include/sa_b200.h) over the CUDA kernels.
+// Host orchestration that replaces alignSequenceGPU.cu:356-653 (initMemory, the
+// per-band launch loop, the D2H drain and the CPU traceback).  No CPU fallback:
+// every compute entry fails with SA_ERR_NO_DEVICE when there is no GPU.
+#include "../../include/sa_b200.h"
+#include "sa_batch.cuh"
+#include "sa_long.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace sa;
+
+namespace {
+
+#define SA_TRY(expr, code)                                        \
+    do {                                                          \
+        cudaError_t e__ = (expr);                                 \
+        if (e__ != cudaSuccess) { ctx->last_cuda = (int)e__; return (code); } \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+constexpr int NSLOT = 3;   // pipeline depth of the host batch path
+
+struct Slot {              // per-chunk device buffers of the host batch path
+    cudaStream_t stream = nullptr;
+    DevBuf text, pattern, toff, poff, results, alnoff, outT, outP, dirs, fill, order;
+    cudaEvent_t done = nullptr;
+};
+
+} // namespace
+
+struct sa_context {
+    int device = 0;
+    int sms = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // scoring tables on the device
+    DevBuf dS4, dS;
+    // single-pair / device-batch workspaces
+    DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf;
+    PinBuf pin;
+    Slot slot[NSLOT];
+    uint32_t epoch = 0;
+    size_t rowbuf_entries_valid = 0;
+    sa_timing timing = {};
+    // per-kernel timing: (before fill, after fill, after traceback) event triples of the last call
+    std::vector<cudaEvent_t> evpool;
+    size_t evused = 0;
+    bool timing_dirty = false;
+    int last_cuda = 0;
+    size_t dirs_budget = (size_t)6 << 30;   // bytes of direction workspace per chunk
+};
+
+namespace {
+
+double ev_us(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+    return (double)ms * 1000.0;
+}
+
+cudaEvent_t next_event(sa_context *ctx)
+{
+    if (ctx->evused == ctx->evpool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        ctx->evpool.push_back(e);
+    }
+    return ctx->evpool[ctx->evused++];
+}
+
+void reset_timing(sa_context *ctx)
+{
+    ctx->timing = sa_timing{};
+    ctx->evused = 0;
+    ctx->timing_dirty = false;
+}
+
+// ------------------------------------------------------------------ scoring tables
+int upload_scoring(sa_context *ctx, const sa_scoring *sc, cudaStream_t st)
+{
+    if (!sc || !sc->score_matrix || !sc->alphabet) return SA_ERR_ARGUMENT;
+    if (sc->alphabet_size < 2 || sc->alphabet_size > MAX_ALPHA) return SA_ERR_ARGUMENT;
+    if (sc->mode != SA_GLOBAL && sc->mode != SA_LOCAL) return SA_ERR_ARGUMENT;
+    if (sc->gap < 0 || sc->gap > (1 << 24)) return SA_ERR_SCORE_RANGE;
+    const int a = sc->alphabet_size;
+    int8_t h4[32 * MAX_ALPHA];
+    int32_t hs[MAX_ALPHA * MAX_ALPHA];
+    std::memset(h4, 0, sizeof h4);
+    for (int p = 0; p < a; ++p)
+        for (int t = 0; t < a; ++t) {
+            const int v = sc->score_matrix[p * a + t];
+            if (v * SCALE < -127 || v * SCALE > 127) return SA_ERR_SCORE_RANGE;   // IDP.4A byte profile
+            h4[p * 32 + t] = (int8_t)(v * SCALE);
+            hs[p * a + t] = v;
+        }
+    SA_TRY(ctx->dS4.reserve(sizeof h4), SA_ERR_MEMORY);
+    SA_TRY(ctx->dS.reserve(sizeof hs), SA_ERR_MEMORY);
+    SA_TRY(cudaMemcpyAsync(ctx->dS4.p, h4, sizeof h4, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
+    SA_TRY(cudaMemcpyAsync(ctx->dS.p, hs, sizeof(int32_t) * a * a, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
+    // the two small host arrays live on this stack frame: make the copies complete before returning
+    SA_TRY(cudaStreamSynchronize(st), SA_ERR_COPY);
+    return SA_OK;
+}
+
+// ------------------------------------------------------------------ batch kernel dispatch
+struct BatchCfg { int R, L; };
+
+// Default classes: rows covered = R*L.  Short patterns use 16-lane groups (2 pairs per warp),
+// longer ones a whole warp per pair.  SA_BATCH_CLASSES="R,L;R,L;..." overrides (dev tool).
+const BatchCfg kBatchCfgs[] = {{8, 16}, {12, 16}, {16, 16}, {20, 16}, {24, 16}, {16, 32}, {24, 32}, {32, 32}, {48, 32}};
+// every instantiation of batch_fill_kernel
+#define SA_BATCH_CFG_LIST(X) X(8, 8) X(16, 8) X(32, 8) X(40, 8) X(48, 8) X(8, 16) X(12, 16) X(16, 16) X(20, 16) X(24, 16) \
+    X(8, 32) X(10, 32) X(12, 32) X(16, 32) X(24, 32) X(32, 32) X(48, 32)
+constexpr int BATCH_WARPS = 4;   // warps per block
+constexpr uint32_t BATCH_MAX_TEXT = 16384;
+constexpr uint32_t BATCH_MAX_ROWS = 1536;
+
+bool cfg_exists(int R, int L)
+{
+#define X(r, l) if (R == r && L == l) return true;
+    SA_BATCH_CFG_LIST(X)
+#undef X
+    return false;
+}
+
+size_t batch_task_stride(const BatchCfg &c, uint32_t max_n)
+{
+    const int CB = cb_for(c.R), NW = c.R * CB / 16;
+    const size_t nblocks = ((size_t)max_n + c.L - 1 + CB - 1) / CB;
+    return nblocks * NW * 32;
+}
+
+size_t batch_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n, bool local)
+{
+    const int G = 32 / c.L;
+    const size_t group = ((size_t)alpha * c.L * rpad_for(c.R) + ((max_n + 15u) & ~15u) + 15u) & ~(size_t)15;
+    const size_t snap = local ? (size_t)((c.R + 3) / 4) * 32 * 16 + 16 * G : 0;
+    return 32 * MAX_ALPHA + (size_t)BATCH_WARPS * (G * group + snap);
+}
+
+// Classes needed for patterns up to max_m and texts up to max_n.  Returns false if max_m is not covered.
+bool build_class_table(uint32_t max_n, uint32_t max_m, BatchClassTable *T)
+{
+    std::vector<BatchCfg> cfgs;
+    if (const char *e = std::getenv("SA_BATCH_CLASSES")) {
+        int R = 0, L = 0, used = 0;
+        const char *q = e;
+        while (std::sscanf(q, "%d,%d%n", &R, &L, &used) == 2) {
+            if (cfg_exists(R, L)) cfgs.push_back(BatchCfg{R, L});
+            q += used;
+            if (*q == ';') ++q; else break;
+        }
+        std::sort(cfgs.begin(), cfgs.end(), [](const BatchCfg &x, const BatchCfg &y) { return x.R * x.L < y.R * y.L; });
+    }
+    if (cfgs.empty() || (uint32_t)(cfgs.back().R * cfgs.back().L) < max_m)
+        cfgs.assign(std::begin(kBatchCfgs), std::end(kBatchCfgs));
+    std::memset(T, 0, sizeof *T);
+    for (const BatchCfg &c : cfgs) {
+        if (T->n_classes == MAX_CLASSES) break;
+        const int k = T->n_classes++;
+        T->R[k] = c.R; T->L[k] = c.L; T->max_rows[k] = (uint32_t)(c.R * c.L);
+        T->stride[k] = batch_task_stride(c, max_n);
+        if ((uint32_t)(c.R * c.L) >= max_m) break;      // larger classes cannot occur
+    }
+    T->max_text = BATCH_MAX_TEXT;
+    int shift = 0;
+    while ((max_n >> shift) >= (uint32_t)SORT_BUCKETS) ++shift;
+    T->bucket_shift = shift;
+    return T->n_classes > 0 && T->max_rows[T->n_classes - 1] >= max_m;
+}
+
+// upper bound of the direction words a chunk of `count` pairs can need
+size_t batch_dirs_bound(const BatchClassTable &T, uint64_t count)
+{
+    double perPair = 0;
+    size_t round = 0;
+    for (int c = 0; c < T.n_classes; ++c) {
+        perPair = std::max(perPair, (double)T.stride[c] / (32 / T.L[c]));
+        round += T.stride[c];
+    }
+    return (size_t)(perPair * (double)count) + round + 64;
+}
+
+size_t batch_sort_bytes(uint64_t count) { return (size_t)MAX_CLASSES * SORT_BUCKETS * 4 + count * 8 + (MAX_CLASSES + 1) * sizeof(BatchClassDyn) + 256; }
+
+template <int R, int L>
+cudaError_t launch_batch_fill_t(const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+{
+    if (local) batch_fill_kernel<R, L, true, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A);
+    else batch_fill_kernel<R, L, false, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+template <int R, int L>
+int occupancy_batch_t(bool local, size_t smem)
+{
+    int nb = 0;
+    // the opt-in shared-memory limit must be raised BEFORE the query, otherwise it reports 0 blocks
+    if (local) {
+        cudaFuncSetAttribute(batch_fill_kernel<R, L, true, BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, batch_fill_kernel<R, L, true, BATCH_WARPS>, BATCH_WARPS * 32, smem);
+    } else {
+        cudaFuncSetAttribute(batch_fill_kernel<R, L, false, BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, batch_fill_kernel<R, L, false, BATCH_WARPS>, BATCH_WARPS * 32, smem);
+    }
+    return nb;
+}
+
+cudaError_t launch_batch_fill(const BatchCfg &cfg, const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+{
+#define X(r, l) if (cfg.R == r && cfg.L == l) return launch_batch_fill_t<r, l>(A, local, grid, smem, st);
+    SA_BATCH_CFG_LIST(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+int occupancy_batch(const BatchCfg &cfg, bool local, size_t smem)
+{
+#define X(r, l) if (cfg.R == r && cfg.L == l) return occupancy_batch_t<r, l>(local, smem);
+    SA_BATCH_CFG_LIST(X)
+#undef X
+    return 0;
+}
+
+// Enqueue binning + fill (one launch per class) + traceback for pairs [first, first+count) of a
+// device-resident batch.  d_dirs: direction workspace (dirs_words words); d_fill: score/end_i/end_j
+// (3 x n_pairs x 4 B); d_sort: batch_sort_bytes(count) bytes.  Pairs whose pattern exceeds
+// BATCH_MAX_ROWS or whose text exceeds BATCH_MAX_TEXT are left untouched (the host path aligns
+// them one by one through the long-pair kernels).
+int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_result *d_results,
+                  uint64_t *d_alnoff, char *d_outT, char *d_outP, uint32_t max_n, uint32_t max_m,
+                  uint32_t *d_dirs, size_t dirs_words, void *d_fill, void *d_sort, cudaStream_t st,
+                  uint32_t first, uint32_t count)
+{
+    BatchClassTable T;
+    if (max_n > BATCH_MAX_TEXT || !build_class_table(max_n, std::min(max_m, BATCH_MAX_ROWS), &T)) return SA_ERR_ARGUMENT;
+    if (batch_dirs_bound(T, count) > dirs_words) return SA_ERR_MEMORY;
+    const bool local = sc->mode == SA_LOCAL;
+
+    int32_t *d_score = reinterpret_cast<int32_t *>(d_fill);
+    uint32_t *d_ei = reinterpret_cast<uint32_t *>(d_fill) + b->n_pairs;
+    uint32_t *d_ej = reinterpret_cast<uint32_t *>(d_fill) + 2 * b->n_pairs;
+
+    // ---- binning (counting sort by class and descending text length) ----
+    BatchSortArgs S{};
+    S.text_off = b->text_off; S.pattern_off = b->pattern_off; S.base = first; S.count = count; S.table = T;
+    S.hist = reinterpret_cast<uint32_t *>(d_sort);
+    S.key = S.hist + MAX_CLASSES * SORT_BUCKETS;
+    S.order = S.key + count;
+    S.dyn = reinterpret_cast<BatchClassDyn *>(reinterpret_cast<char *>(S.order + count) + ((8 - ((uintptr_t)(S.order + count) & 7)) & 7));
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx);
+    cudaEventRecord(e0, st);
+    SA_TRY(cudaMemsetAsync(S.hist, 0, (size_t)MAX_CLASSES * SORT_BUCKETS * 4, st), SA_ERR_LAUNCH);
+    batch_classify_kernel<<<(count + 255) / 256, 256, 0, st>>>(S);
+    batch_scan_kernel<<<1, 1024, 0, st>>>(S);
+    batch_scatter_kernel<<<(count + 255) / 256, 256, 0, st>>>(S);
+    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    ctx->timing.kernel_launches += 3;
+
+    // ---- fill: one launch per class; empty classes exit at once ----
+    for (int c = 0; c < T.n_classes; ++c) {
+        const BatchCfg cfg{T.R[c], T.L[c]};
+        const int G = 32 / cfg.L;
+        const size_t smem = batch_smem_bytes(cfg, sc->alphabet_size, max_n, local);
+        if (smem > (size_t)ctx->smem_optin) return SA_ERR_ARGUMENT;
+        BatchArgs A{};
+        A.text = b->text; A.text_off = b->text_off; A.pattern = b->pattern; A.pattern_off = b->pattern_off;
+        A.order = S.order; A.dyn = S.dyn + c; A.dirs = d_dirs; A.task_stride = T.stride[c];
+        A.score = d_score; A.end_i = d_ei; A.end_j = d_ej;
+        A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap; A.max_n = max_n;
+        int occ = occupancy_batch(cfg, local, smem);
+        if (occ < 1) return SA_ERR_LAUNCH;
+        const uint64_t nTasksMax = ((uint64_t)count + G - 1) / G;
+        int grid = (int)std::min<uint64_t>((uint64_t)ctx->sms * occ, (nTasksMax + BATCH_WARPS - 1) / BATCH_WARPS);
+        if (grid < 1) grid = 1;
+        SA_TRY(launch_batch_fill(cfg, A, local, grid, smem, st), SA_ERR_LAUNCH);
+        ctx->timing.kernel_launches++;
+    }
+    cudaEventRecord(e1, st);
+
+    BatchTraceArgs R{};
+    R.text = b->text; R.text_off = b->text_off; R.pattern = b->pattern; R.pattern_off = b->pattern_off;
+    R.order = S.order; R.dyn = S.dyn; R.table = T; R.dirs = d_dirs;
+    R.score = d_score; R.end_i = d_ei; R.end_j = d_ej;
+    R.S = ctx->dS.as<int32_t>(); R.alpha = sc->alphabet_size; R.gap = sc->gap; R.local = local;
+    std::memcpy(R.alphabet, sc->alphabet, sc->alphabet_size + 1);
+    R.results = d_results; R.aln_off = d_alnoff; R.out_text = d_outT; R.out_pattern = d_outP;
+    batch_traceback_kernel<<<(count + 127) / 128, 128, 0, st>>>(R);
+    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    cudaEventRecord(e2, st);
+    ctx->timing.kernel_launches++;
+    ctx->timing_dirty = true;
+    return SA_OK;
+}
+
+// ------------------------------------------------------------------ long-pair dispatch
+constexpr int LONG_WARPS = 4;
+const int kLongR[] = {4, 6, 8, 12, 16};
+
+template <int R>
+cudaError_t launch_long_t(const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+{
+    void *args[] = {(void *)&A};
+    cudaError_t e;
+    const void *fn = local ? (const void *)long_fill_kernel<R, true, LONG_WARPS> : (const void *)long_fill_kernel<R, false, LONG_WARPS>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LONG_WARPS * 32), args, smem, st);
+}
+template <int R>
+int occupancy_long_t(bool local, size_t smem)
+{
+    int nb = 0;
+    const void *fn = local ? (const void *)long_fill_kernel<R, true, LONG_WARPS> : (const void *)long_fill_kernel<R, false, LONG_WARPS>;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, LONG_WARPS * 32, smem);
+    return nb;
+}
+#define LONG_DISPATCH(FN, ...)                       \
+    switch (R) {                                     \
+    case 4: return FN<4>(__VA_ARGS__);               \
+    case 6: return FN<6>(__VA_ARGS__);               \
+    case 8: return FN<8>(__VA_ARGS__);               \
+    case 12: return FN<12>(__VA_ARGS__);             \
+    case 16: return FN<16>(__VA_ARGS__);             \
+    }
+cudaError_t launch_long(int R, const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+{
+    LONG_DISPATCH(launch_long_t, A, local, grid, smem, st);
+    return cudaErrorInvalidValue;
+}
+int occupancy_long(int R, bool local, size_t smem)
+{
+    LONG_DISPATCH(occupancy_long_t, local, smem);
+    return 0;
+}
+
+struct LongPlan {
+    int R, CB, NW, grid;
+    uint32_t n_strips, ring;
+    size_t strip_stride, row_stride, smem;
+};
+
+int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P)
+{
+    const bool local = sc->mode == SA_LOCAL;
+    const uint64_t targetWarps = (uint64_t)ctx->sms * 4;      // one warp per SM sub-partition
+    int R = kLongR[sizeof(kLongR) / sizeof(int) - 1];
+    for (int r : kLongR)
+        if ((m + 32ull * r - 1) / (32ull * r) <= targetWarps) { R = r; break; }
+    if (const char *e = std::getenv("SA_LONG_R")) {
+        const int r = std::atoi(e);
+        for (int k : kLongR) if (k == r) R = r;
+    }
+    P->R = R; P->CB = cb_for(R); P->NW = R * P->CB / 16;
+    P->n_strips = (uint32_t)((m + 32ull * R - 1) / (32ull * R));
+    P->smem = 32 * MAX_ALPHA + (size_t)LONG_WARPS * ((size_t)sc->alphabet_size * 32 * rpad_for(R) + (local ? ((R + 3) / 4) * 32 * 16 : 0));
+    int occ = occupancy_long(R, local, P->smem);
+    if (occ < 1) return SA_ERR_LAUNCH;
+    const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
+    const uint64_t needBlocks = (P->n_strips + LONG_WARPS - 1) / LONG_WARPS;
+    P->grid = (int)std::min(maxBlocks, needBlocks);
+    const uint64_t W = (uint64_t)P->grid * LONG_WARPS;
+    P->ring = (uint32_t)std::min<uint64_t>(P->n_strips, W + 1);
+    P->row_stride = (n + 63) & ~(size_t)63;
+    const size_t nblocks = (n + 31 + P->CB - 1) / P->CB;
+    P->strip_stride = nblocks * P->NW * 32;
+    return SA_OK;
+}
+
+// Align one long pair whose sequences are already on the device.  Results (len, starts) land
+// in ctx->misc (device) and are read back by the caller.
+int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n,
+                 const uint8_t *d_pat, uint64_t m, char *d_outT, char *d_outP, uint64_t cap,
+                 bool traceback, cudaStream_t st)
+{
+    LongPlan P;
+    int rc = plan_long(ctx, sc, n, m, &P);
+    if (rc) return rc;
+    const bool local = sc->mode == SA_LOCAL;
+    SA_TRY(ctx->dirs.reserve((size_t)P.n_strips * P.strip_stride * 4), SA_ERR_MEMORY);
+    const size_t rowEntries = (size_t)P.ring * P.row_stride;
+    const bool fresh = rowEntries * 8 > ctx->rowbuf.cap;
+    SA_TRY(ctx->rowbuf.reserve(rowEntries * 8), SA_ERR_MEMORY);
+    // tags carry a per-call epoch so the ring never needs clearing between calls
+    ctx->epoch = (ctx->epoch + 1) & 0x7ff;
+    if (fresh || ctx->epoch == 0) {
+        SA_TRY(cudaMemsetAsync(ctx->rowbuf.p, 0, ctx->rowbuf.cap, st), SA_ERR_LAUNCH);
+        if (ctx->epoch == 0) ctx->epoch = 1;
+    }
+    // misc layout: [0..3] u64 res, then score(int), then cand arrays
+    const size_t miscBytes = 64 + (size_t)P.n_strips * 12 + 64;   // [48..51] = gmax
+    SA_TRY(ctx->misc.reserve(miscBytes), SA_ERR_MEMORY);
+    uint64_t *d_res = ctx->misc.as<uint64_t>();
+    int32_t *d_score = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 32);
+    int *d_cv = reinterpret_cast<int *>(ctx->misc.as<char>() + 64);
+    uint32_t *d_ci = reinterpret_cast<uint32_t *>(d_cv + P.n_strips);
+    uint32_t *d_cj = d_ci + P.n_strips;
+
+    LongArgs A{};
+    A.text = d_text; A.n = (uint32_t)n; A.pattern = d_pat; A.m = (uint32_t)m;
+    A.dirs = ctx->dirs.as<uint32_t>(); A.strip_stride = P.strip_stride;
+    A.rowbuf = ctx->rowbuf.as<unsigned long long>(); A.ring = P.ring; A.row_stride = P.row_stride;
+    A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap;
+    A.n_strips = P.n_strips; A.left_col = nullptr; A.right_col = nullptr; A.col0 = 0;
+    A.score = d_score; A.cand_v = d_cv; A.cand_i = d_ci; A.cand_j = d_cj;
+    A.tag_base = (uint32_t)ctx->epoch << 21;
+    A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
+    SA_TRY(cudaMemsetAsync(A.gmax, 0, 4, st), SA_ERR_LAUNCH);
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx);
+    cudaEventRecord(e0, st);
+    SA_TRY(launch_long(P.R, A, local, P.grid, P.smem, st), SA_ERR_LAUNCH);
+    cudaEventRecord(e1, st);
+    ctx->timing.kernel_launches++;
+
+    LongTraceArgs T{};
+    T.text = d_text; T.n = (uint32_t)n; T.pattern = d_pat; T.m = (uint32_t)m;
+    T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = P.strip_stride;
+    T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
+    T.R = P.R; T.CB = P.CB; T.n_strips = P.n_strips;
+    T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
+    std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
+    T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
+    T.emit = traceback ? 1 : 0;
+    long_traceback_kernel<<<1, 32, 0, st>>>(T);
+    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    cudaEventRecord(e2, st);
+    ctx->timing.kernel_launches++;
+    ctx->timing_dirty = true;
+    return SA_OK;
+}
+
+// members of a batch that the batch kernels can take (the device-side classifier applies the same rule)
+bool batch_eligible(uint64_t n, uint64_t m) { return m <= BATCH_MAX_ROWS && n <= BATCH_MAX_TEXT; }
+
+// routing of a SINGLE pair: small ones ride the batch kernels, everything else the strip kernel
+bool use_batch_path(uint64_t n, uint64_t m)
+{
+    if (const char *e = std::getenv("SA_FORCE_PATH")) {
+        if (!std::strcmp(e, "long")) return false;
+        if (!std::strcmp(e, "batch")) return batch_eligible(n, m);
+    }
+    return m <= 384 && n <= 4096;
+}
+
+} // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char *sa_version(void) { return "sa_b200 0.1 (sm_100a)"; }
+
+const char *sa_status_string(int s)
+{
+    switch (s) {
+    case SA_OK: return "ok";
+    case SA_ERR_NO_DEVICE: return "no CUDA device";
+    case SA_ERR_MEMORY: return "sequence is too long, not enough memory";
+    case SA_ERR_COPY: return "could not copy to/from device memory";
+    case SA_ERR_ARGUMENT: return "invalid argument";
+    case SA_ERR_SCORE_RANGE: return "score matrix / gap outside the supported range";
+    case SA_ERR_LAUNCH: return "kernel launch failed";
+    case SA_ERR_CAPACITY: return "output buffer too small";
+    }
+    return "unknown";
+}
+
+int sa_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sa_create(int device, sa_context **out)
+{
+    if (!out) return SA_ERR_ARGUMENT;
+    *out = nullptr;
+    if (device < 0 || device >= sa_device_count()) return SA_ERR_NO_DEVICE;
+    sa_context *ctx = new (std::nothrow) sa_context();
+    if (!ctx) return SA_ERR_MEMORY;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return SA_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SA_ERR_NO_DEVICE; }
+    ctx->sms = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SA_ERR_NO_DEVICE; }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &s : ctx->slot) {
+        cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    }
+    if (const char *e = std::getenv("SA_DIRS_BUDGET_MB")) ctx->dirs_budget = (size_t)std::atoll(e) << 20;
+    *out = ctx;
+    return SA_OK;
+}
+
+void sa_destroy(sa_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf})
+        b->release();
+    ctx->pin.release();
+    for (auto &s : ctx->slot) {
+        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order}) b->release();
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->evpool) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sa_last_timing(const sa_context *cctx, sa_timing *out)
+{
+    if (!cctx || !out) return SA_ERR_ARGUMENT;
+    sa_context *ctx = const_cast<sa_context *>(cctx);
+    if (ctx->timing_dirty) {
+        // kernel times from the event triples (valid once the caller has synchronised the stream)
+        double fill = 0, tb = 0;
+        for (size_t i = 0; i + 2 < ctx->evused + 0 && i + 2 < ctx->evpool.size() + 0; i += 3) {
+            if (cudaEventQuery(ctx->evpool[i + 2]) != cudaSuccess) { cudaGetLastError(); return SA_ERR_LAUNCH; }
+            fill += ev_us(ctx->evpool[i], ctx->evpool[i + 1]);
+            tb += ev_us(ctx->evpool[i + 1], ctx->evpool[i + 2]);
+        }
+        ctx->timing.fill_us = fill;
+        ctx->timing.traceback_us = tb;
+        ctx->timing_dirty = false;
+    }
+    *out = ctx->timing;
+    return SA_OK;
+}
+
+int sa_last_cuda_error(const sa_context *ctx) { return ctx ? ctx->last_cuda : 0; }
+
+// --------------------------------------------------------------- single pair
+static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *text, uint64_t n,
+                        const uint8_t *pattern, uint64_t m, sa_result *result, char *outT, char *outP,
+                        uint64_t cap, bool traceback, uint64_t *argmax)
+{
+    if (!ctx) return SA_ERR_ARGUMENT;
+    if (!sc || !text || !pattern || !result || n == 0 || m == 0) return SA_ERR_ARGUMENT;
+    if (n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64) return SA_ERR_ARGUMENT;
+    if (traceback && (!outT || !outP)) return SA_ERR_ARGUMENT;
+    if (traceback && cap < n + m) return SA_ERR_CAPACITY;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaStream_t st = ctx->stream;
+    reset_timing(ctx);
+    ctx->timing.cells = (n + 1) * (m + 1);
+    int rc = upload_scoring(ctx, sc, st);
+    if (rc) return rc;
+
+    const uint64_t slot = n + m;
+    SA_TRY(ctx->dtext.reserve(n + 16), SA_ERR_MEMORY);
+    SA_TRY(ctx->dpat.reserve(m + 16), SA_ERR_MEMORY);
+    SA_TRY(ctx->doutT.reserve(slot + 16), SA_ERR_MEMORY);
+    SA_TRY(ctx->doutP.reserve(slot + 16), SA_ERR_MEMORY);
+    cudaEventRecord(ctx->ev[0], st);
+    SA_TRY(cudaMemcpyAsync(ctx->dtext.p, text, n, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
+    SA_TRY(cudaMemcpyAsync(ctx->dpat.p, pattern, m, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
+    cudaEventRecord(ctx->ev[1], st);
+
+    sa_result hres{};
+    uint64_t hoff = 0, hargmax = 0;
+    if (use_batch_path(n, m)) {
+        // a one-pair batch through the batch kernels
+        SA_TRY(ctx->misc.reserve(256), SA_ERR_MEMORY);
+        int64_t hoffs[4] = {0, (int64_t)n, 0, (int64_t)m};
+        int64_t *d_offs = ctx->misc.as<int64_t>();                 // [0,1]=text_off [2,3]=pattern_off
+        sa_result *d_res = reinterpret_cast<sa_result *>(ctx->misc.as<char>() + 64);
+        uint64_t *d_alnoff = reinterpret_cast<uint64_t *>(ctx->misc.as<char>() + 128);
+        SA_TRY(cudaMemcpyAsync(d_offs, hoffs, sizeof hoffs, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
+        SA_TRY(cudaStreamSynchronize(st), SA_ERR_COPY);
+        BatchClassTable T;
+        if (!build_class_table((uint32_t)n, (uint32_t)m, &T)) return SA_ERR_ARGUMENT;
+        SA_TRY(ctx->dirs.reserve(batch_dirs_bound(T, 1) * 4), SA_ERR_MEMORY);
+        SA_TRY(ctx->fill.reserve(64), SA_ERR_MEMORY);
+        SA_TRY(ctx->sortbuf.reserve(batch_sort_bytes(1)), SA_ERR_MEMORY);
+        sa_batch b{1, ctx->dtext.as<uint8_t>(), d_offs, ctx->dpat.as<uint8_t>(), d_offs + 2};
+        cudaEventRecord(ctx->ev[2], st);
+        rc = enqueue_batch(ctx, sc, &b, d_res, d_alnoff, ctx->doutT.as<char>(), ctx->doutP.as<char>(),
+                           (uint32_t)n, (uint32_t)m, ctx->dirs.as<uint32_t>(), ctx->dirs.cap / 4, ctx->fill.p,
+                           ctx->sortbuf.p, st, 0, 1);
+        if (rc) return rc;
+        cudaEventRecord(ctx->ev[3], st);
+        SA_TRY(cudaMemcpyAsync(&hres, d_res, sizeof hres, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        SA_TRY(cudaMemcpyAsync(&hoff, d_alnoff, 8, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);
+        if (sc->mode == SA_LOCAL) {
+            uint32_t ij[2] = {0, 0};
+            cudaMemcpy(&ij[0], reinterpret_cast<uint32_t *>(ctx->fill.p) + 1, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&ij[1], reinterpret_cast<uint32_t *>(ctx->fill.p) + 2, 4, cudaMemcpyDeviceToHost);
+            hargmax = (uint64_t)ij[0] * (n + 1) + ij[1];
+        }
+    } else {
+        cudaEventRecord(ctx->ev[2], st);
+        rc = enqueue_long(ctx, sc, ctx->dtext.as<uint8_t>(), n, ctx->dpat.as<uint8_t>(), m,
+                          ctx->doutT.as<char>(), ctx->doutP.as<char>(), slot, traceback, st);
+        if (rc) return rc;
+        cudaEventRecord(ctx->ev[3], st);
+        uint64_t hr[4]; int32_t hs = 0;
+        SA_TRY(cudaMemcpyAsync(hr, ctx->misc.p, sizeof hr, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        SA_TRY(cudaMemcpyAsync(&hs, ctx->misc.as<char>() + 32, 4, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);
+        hres.score = hs; hres.aln_len = hr[0]; hres.start_text = hr[1]; hres.start_pattern = hr[2];
+        hoff = slot - hr[0];
+        hargmax = hr[3];
+    }
+    if (traceback && hres.aln_len) {
+        SA_TRY(cudaMemcpyAsync(outT, ctx->doutT.as<char>() + hoff, hres.aln_len, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        SA_TRY(cudaMemcpyAsync(outP, ctx->doutP.as<char>() + hoff, hres.aln_len, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+    }
+    cudaEventRecord(ctx->ev[4], st);
+    SA_TRY(cudaStreamSynchronize(st), SA_ERR_COPY);
+    *result = hres;
+    if (argmax) *argmax = hargmax;
+    ctx->timing.h2d_us = ev_us(ctx->ev[0], ctx->ev[1]);
+    ctx->timing.d2h_us = ev_us(ctx->ev[3], ctx->ev[4]);
+    ctx->timing.total_us = ev_us(ctx->ev[0], ctx->ev[4]);
+    {
+        sa_timing k{};
+        sa_last_timing(ctx, &k);     // folds the per-kernel event triples into fill_us / traceback_us
+    }
+    return SA_OK;
+}
+
+int sa_align(sa_context *ctx, const sa_scoring *sc, const uint8_t *text, uint64_t n, const uint8_t *pattern,
+             uint64_t m, sa_result *result, char *outT, char *outP, uint64_t cap)
+{
+    return align_single(ctx, sc, text, n, pattern, m, result, outT, outP, cap, true, nullptr);
+}
+
+int sa_fill_only(sa_context *ctx, const sa_scoring *sc, const uint8_t *text, uint64_t n, const uint8_t *pattern,
+                 uint64_t m, int32_t *score, uint64_t *argmax)
+{
+    sa_result r{};
+    // long pairs skip the string emission; short ones go through the (cheap) batch traceback
+    if (!ctx) return SA_ERR_ARGUMENT;
+    const uint64_t cap = n + m;
+    std::vector<char> t, p;
+    char *pt = nullptr, *pp = nullptr;
+    if (use_batch_path(n, m)) { t.resize(cap); p.resize(cap); pt = t.data(); pp = p.data(); }
+    int rc = align_single(ctx, sc, text, n, pattern, m, &r, pt, pp, cap, pt != nullptr, argmax);
+    if (rc) return rc;
+    if (score) *score = r.score;
+    return SA_OK;
+}
+
+// Device-resident single pair: sequences, output buffers (capacity n+m each) and the 4-word
+// result {len, start_text, start_pattern, score} are device pointers; enqueued on `stream`.
+int sa_align_device(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n,
+                    const uint8_t *d_pattern, uint64_t m, char *d_outT, char *d_outP, uint64_t *d_result4,
+                    void *stream)
+{
+    if (!ctx || !sc || !d_text || !d_pattern || !d_outT || !d_outP || !d_result4 || n == 0 || m == 0) return SA_ERR_ARGUMENT;
+    if (n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = upload_scoring(ctx, sc, st);
+    if (rc) return rc;
+    reset_timing(ctx);
+    ctx->timing.cells = (n + 1) * (m + 1);
+    rc = enqueue_long(ctx, sc, d_text, n, d_pattern, m, d_outT, d_outP, n + m, true, st);
+    if (rc) return rc;
+    // misc = {len, start_text, start_pattern, argmax} then score at byte 32
+    SA_TRY(cudaMemcpyAsync(d_result4, ctx->misc.p, 24, cudaMemcpyDeviceToDevice, st), SA_ERR_COPY);
+    SA_TRY(cudaMemcpyAsync(d_result4 + 3, ctx->misc.as<char>() + 32, 4, cudaMemcpyDeviceToDevice, st), SA_ERR_COPY);
+    return SA_OK;
+}
+
+// --------------------------------------------------------------- batches
+int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_batch_out *out,
+                          uint32_t max_n, uint32_t max_m, void *stream)
+{
+    if (!ctx || !sc || !b || !out || !b->text || !b->pattern || !b->text_off || !b->pattern_off ||
+        !out->results || !out->aln_off || !out->aligned_text || !out->aligned_pattern)
+        return SA_ERR_ARGUMENT;
+    if (b->n_pairs == 0) return SA_OK;
+    if (b->n_pairs >= (1ull << 31)) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = upload_scoring(ctx, sc, st);
+    if (rc) return rc;
+    BatchClassTable T;
+    if (max_n > BATCH_MAX_TEXT || max_m > BATCH_MAX_ROWS || !build_class_table(max_n, max_m, &T)) return SA_ERR_ARGUMENT;
+    // chunk so that the direction workspace stays within the budget
+    const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;      // bytes per pair
+    uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / perPair));
+    chunk = std::min<uint64_t>(chunk, b->n_pairs);
+    SA_TRY(ctx->dirs.reserve(batch_dirs_bound(T, chunk) * 4), SA_ERR_MEMORY);
+    SA_TRY(ctx->fill.reserve(b->n_pairs * 12 + 64), SA_ERR_MEMORY);
+    SA_TRY(ctx->sortbuf.reserve(batch_sort_bytes(chunk)), SA_ERR_MEMORY);
+    reset_timing(ctx);
+    cudaEventRecord(ctx->ev[2], st);
+    for (uint64_t first = 0; first < b->n_pairs; first += chunk) {
+        const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, b->n_pairs - first);
+        rc = enqueue_batch(ctx, sc, b, out->results, out->aln_off, out->aligned_text, out->aligned_pattern,
+                           max_n, max_m, ctx->dirs.as<uint32_t>(), ctx->dirs.cap / 4, ctx->fill.p, ctx->sortbuf.p, st,
+                           (uint32_t)first, count);
+        if (rc) return rc;
+    }
+    cudaEventRecord(ctx->ev[3], st);
+    return SA_OK;
+}
+
+int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_batch_out *out)
+{
+    if (!ctx || !sc || !b || !out || !b->text || !b->pattern || !b->text_off || !b->pattern_off ||
+        !out->results || !out->aln_off || !out->aligned_text || !out->aligned_pattern)
+        return SA_ERR_ARGUMENT;
+    const uint64_t N = b->n_pairs;
+    if (N == 0) return SA_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    const int64_t *to = b->text_off, *po = b->pattern_off;
+    if ((uint64_t)(to[N] - to[0] + po[N] - po[0]) > out->arena_capacity) return SA_ERR_CAPACITY;
+
+    // pairs too long for the batch kernels are aligned one by one through sa_align
+    uint32_t max_n = 0, max_m = 0;
+    uint64_t cells = 0;
+    std::vector<uint64_t> longPairs;
+    for (uint64_t p = 0; p < N; ++p) {
+        const uint64_t n = (uint64_t)(to[p + 1] - to[p]), m = (uint64_t)(po[p + 1] - po[p]);
+        if (n == 0 || m == 0) return SA_ERR_ARGUMENT;
+        cells += (n + 1) * (m + 1);
+        if (!batch_eligible(n, m)) { longPairs.push_back(p); continue; }
+        max_n = std::max<uint32_t>(max_n, (uint32_t)n);
+        max_m = std::max<uint32_t>(max_m, (uint32_t)m);
+    }
+    int rc = upload_scoring(ctx, sc, ctx->stream);
+    if (rc) return rc;
+    reset_timing(ctx);
+    sa_timing tm{};
+    tm.cells = cells;
+
+    if (max_m > 0) {
+        BatchClassTable T;
+        if (!build_class_table(max_n, max_m, &T)) return SA_ERR_ARGUMENT;
+        // chunk size: bounded by the direction budget and by ~1/8 of the batch for copy/compute overlap
+        const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;
+        uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / NSLOT / perPair));
+        chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, (N + 7) / 8));
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        for (auto &s : ctx->slot) cudaStreamWaitEvent(s.stream, ctx->ev[0], 0);
+        int si = 0;
+        for (uint64_t first = 0; first < N; first += chunk, si = (si + 1) % NSLOT) {
+            Slot &s = ctx->slot[si];
+            const uint64_t count = std::min<uint64_t>(chunk, N - first);
+            const int64_t tb = to[first], pb = po[first];
+            const uint64_t tbytes = (uint64_t)(to[first + count] - tb), pbytes = (uint64_t)(po[first + count] - pb);
+            const uint64_t arena = tbytes + pbytes;
+            // wait until this slot's previous chunk has fully drained
+            SA_TRY(cudaEventSynchronize(s.done), SA_ERR_LAUNCH);
+            SA_TRY(s.text.reserve(tbytes + 16), SA_ERR_MEMORY);
+            SA_TRY(s.pattern.reserve(pbytes + 16), SA_ERR_MEMORY);
+            SA_TRY(s.toff.reserve((count + 1) * 8), SA_ERR_MEMORY);
+            SA_TRY(s.poff.reserve((count + 1) * 8), SA_ERR_MEMORY);
+            SA_TRY(s.results.reserve(count * sizeof(sa_result)), SA_ERR_MEMORY);
+            SA_TRY(s.alnoff.reserve(count * 8), SA_ERR_MEMORY);
+            SA_TRY(s.outT.reserve(arena + 16), SA_ERR_MEMORY);
+            SA_TRY(s.outP.reserve(arena + 16), SA_ERR_MEMORY);
+            SA_TRY(s.dirs.reserve(batch_dirs_bound(T, count) * 4), SA_ERR_MEMORY);
+            SA_TRY(s.fill.reserve(count * 12 + 64), SA_ERR_MEMORY);
+            SA_TRY(s.order.reserve(batch_sort_bytes(count)), SA_ERR_MEMORY);
+            SA_TRY(cudaMemcpyAsync(s.text.p, b->text + tb, tbytes, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaMemcpyAsync(s.pattern.p, b->pattern + pb, pbytes, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaMemcpyAsync(s.toff.p, to + first, (count + 1) * 8, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaMemcpyAsync(s.poff.p, po + first, (count + 1) * 8, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
+            // device-side offsets are relative to the chunk: rebase with a tiny kernel-free trick --
+            // the kernels subtract nothing, so pass pointers shifted by the chunk base instead.
+            sa_batch cb{count, s.text.as<uint8_t>() - tb, s.toff.as<int64_t>(), s.pattern.as<uint8_t>() - pb, s.poff.as<int64_t>()};
+            // output slots are addressed by text_off+pattern_off as well: shift the arenas likewise
+            char *oT = s.outT.as<char>() - (tb + pb), *oP = s.outP.as<char>() - (tb + pb);
+            // members too long for the batch kernels are skipped by the device-side classifier
+            // (and aligned one by one below)
+            rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
+                               s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, s.stream, 0, (uint32_t)count);
+            if (rc) return rc;
+            SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaMemcpyAsync(out->aligned_text + (tb - to[0]) + (pb - po[0]), s.outT.p, arena, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaMemcpyAsync(out->aligned_pattern + (tb - to[0]) + (pb - po[0]), s.outP.p, arena, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
+            SA_TRY(cudaEventRecord(s.done, s.stream), SA_ERR_LAUNCH);
+        }
+        for (auto &s : ctx->slot) SA_TRY(cudaStreamSynchronize(s.stream), SA_ERR_LAUNCH);
+        cudaEventRecord(ctx->ev[4], ctx->stream);
+        SA_TRY(cudaStreamSynchronize(ctx->stream), SA_ERR_LAUNCH);
+        tm.total_us = ev_us(ctx->ev[0], ctx->ev[4]);
+        {
+            sa_timing k{};
+            sa_last_timing(ctx, &k);
+            tm.fill_us = k.fill_us; tm.traceback_us = k.traceback_us; tm.kernel_launches = k.kernel_launches;
+        }
+        // aln_off values are absolute (text_off+pattern_off based); make them relative to the arenas
+        const uint64_t base0 = (uint64_t)(to[0] + po[0]);
+        if (base0) for (uint64_t p = 0; p < N; ++p) out->aln_off[p] -= base0;
+    }
+    for (uint64_t p : longPairs) {
+        const uint64_t n = (uint64_t)(to[p + 1] - to[p]), m = (uint64_t)(po[p + 1] - po[p]);
+        const uint64_t slot = (uint64_t)(to[p] - to[0]) + (uint64_t)(po[p] - po[0]);
+        rc = sa_align(ctx, sc, b->text + to[p], n, b->pattern + po[p], m, &out->results[p],
+                      out->aligned_text + slot, out->aligned_pattern + slot, n + m);
+        if (rc) return rc;
+        out->aln_off[p] = slot;
+        sa_timing k{};
+        sa_last_timing(ctx, &k);
+        tm.total_us += k.total_us; tm.fill_us += k.fill_us; tm.traceback_us += k.traceback_us;
+        tm.kernel_launches += k.kernel_launches;
+    }
+    ctx->timing = tm;
+    ctx->timing_dirty = false;
+    return SA_OK;
+}
+
+int sa_partition_batch(const int64_t *to, const int64_t *po, uint64_t N, int world, uint64_t *first)
+{
+    if (!to || !po || !first || world < 1) return SA_ERR_ARGUMENT;
+    // prefix of cells; rank r takes the pairs whose cumulative cell count falls in its 1/world share
+    long double total = 0;
+    for (uint64_t p = 0; p < N; ++p) total += (long double)(to[p + 1] - to[p] + 1) * (long double)(po[p + 1] - po[p] + 1);
+    first[0] = 0;
+    long double acc = 0;
+    uint64_t p = 0;
+    for (int r = 1; r < world; ++r) {
+        const long double target = total * r / world;
+        while (p < N && acc + (long double)(to[p + 1] - to[p] + 1) * (long double)(po[p + 1] - po[p] + 1) / 2 <= target) {
+            acc += (long double)(to[p + 1] - to[p] + 1) * (long double)(po[p + 1] - po[p] + 1);
+            ++p;
+        }
+        first[r] = p;
+    }
+    first[world] = N;
+    return SA_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,307 @@
+// sa_long.cuh -- one long pair (BASELINE configs 1-3, and each GPU's column strip of config 5).
+//
+// The (m+1) x (n+1) matrix is cut into horizontal STRIPS of 32*R rows.  A strip is swept left to
+// right by one warp exactly like a batch group with L = 32 (lane l owns R rows, one __shfl_up per
+// step).  All strips form ONE systolic chain: strip s consumes the bottom row of strip s-1 a few
+// columns behind its producer.  The kernel is persistent and cooperative (every warp resident):
+// warp w sweeps strips w, w+W, w+2W, ... so the chain never deadlocks.
+//
+// Tile-boundary H rows pass through HBM/L2 as 64-bit {4*H, tag} words (tag = strip id + 1): the
+// 8-byte store is atomic, so the consumer needs no fence and no separate flag -- it polls the data
+// word itself (the cross-strip analogue of the reference's columnState hand-off,
+// alignSequenceGPU.cu:14-40, without the per-column atomics).  Rows live in a ring of W+1 buffers.
+//
+// Directions: same warp-step-major packed 2-bit layout as the batch kernel, one region per strip:
+//     word(s, kb, w, lane) at s*stripStride + (kb*NW + w)*32 + lane,   kb = step / CB.
+#pragma once
+#include "sa_cell.cuh"
+
+namespace sa {
+
+struct LongArgs {
+    const uint8_t *text;     uint32_t n;        // this launch's text slice (columns)
+    const uint8_t *pattern;  uint32_t m;
+    uint32_t *dirs;          uint64_t strip_stride;     // words per strip
+    unsigned long long *rowbuf;  uint32_t ring;  uint64_t row_stride;   // ring x row_stride entries
+    const int8_t *S4;        // 32x32 bytes, 4*S[p][t]
+    int alpha, gap;
+    uint32_t n_strips;
+    // Left border of this column slice (multi-GPU strips): nullptr => the matrix border.
+    // left_col[i] = 4*H(i, col0) for DP rows i = 0..m  (col0 = first DP column of the slice minus 1)
+    const int *left_col;
+    int *right_col;          // optional output: 4*H(i, last column) for i = 0..m
+    uint32_t col0;           // global DP column index of the slice's column 0 (for NW borders / arg-max)
+    // results
+    int32_t *score;          // NW: H(m, n) of this slice
+    int *cand_v; uint32_t *cand_i; uint32_t *cand_j;   // SW: per-strip arg-max candidates
+    uint32_t tag_base;       // per-call epoch << 21: ring entries of earlier calls never match
+    int *gmax;               // SW: running alignment-wide maximum (4*H), zeroed per call
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr int PB = 8;   // boundary-row prefetch block (columns)
+
+template <int R, bool LOCAL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
+{
+    static_assert(R % 2 == 0, "R must be even");
+    constexpr int CB = cb_for(R);
+    constexpr int NW = R * CB / 16;
+    constexpr int RPAD = rpad_for(R);
+    constexpr int PS = 32 * RPAD;
+    constexpr int NPW = (R + 3) / 4;
+    constexpr int ROWS = 32 * R;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int alpha = A.alpha;
+    int8_t *S4s = reinterpret_cast<int8_t *>(smem);
+    constexpr uint32_t snapBytes = LOCAL ? ((R + 3) / 4) * 32 * 16 : 0;
+    unsigned char *profS = smem + 32 * MAX_ALPHA + (size_t)warp * (alpha * PS + snapBytes);
+    uint4 *snap = reinterpret_cast<uint4 *>(profS + alpha * PS);
+    for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
+    __syncthreads();
+
+    const int KL = 2 - SCALE * A.gap, KT = 1 - SCALE * A.gap;
+    const uint32_t W = gridDim.x * WARPS;
+    const int n = (int)A.n, m = (int)A.m;
+    const int nSteps = n + 31;
+
+    for (uint32_t s = blockIdx.x * WARPS + warp; s < A.n_strips; s += W) {
+        const int row0 = (int)s * ROWS;                 // pattern index of the strip's first row
+        // ---- query profile of this strip ----
+        __syncwarp();
+        for (int i = lane; i < ROWS; i += 32) {
+            const int off = (i / R) * RPAD + (i % R);
+            const int gi = row0 + i;
+            if (gi < m) {
+                const int8_t *srow = S4s + 32 * min((int)A.pattern[gi], alpha - 1);
+                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)srow[a];
+            } else {
+                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)0x80;
+            }
+        }
+        __syncwarp();
+
+        // ---- boundary state (left border of the slice) ----
+        int c[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gi = row0 + lane * R + r + 1;     // DP row
+            if (A.left_col) c[r] = gi <= m ? A.left_col[gi] : 0;
+            else c[r] = LOCAL ? 0 : -SCALE * A.gap * gi;
+        }
+        int prevTop;                                    // 4*H(i0-1, col0)
+        {
+            const int gi = row0 + lane * R;
+            if (A.left_col) prevTop = gi <= m ? A.left_col[gi] : 0;
+            else prevTop = LOCAL ? 0 : -SCALE * A.gap * gi;
+        }
+        int bottom = 0;
+        int bestv = 0, besti = 0, bestj = 0;
+        int gmCached = 0;                               // lane-local copy of *A.gmax (a lower bound)
+        const bool hasUp = s > 0, hasDown = s + 1 < A.n_strips;
+        const unsigned long long *rowIn = A.rowbuf + (size_t)((s + A.ring - 1) % A.ring) * A.row_stride;
+        unsigned long long *rowOut = A.rowbuf + (size_t)(s % A.ring) * A.row_stride;
+        const unsigned long long wantTag = (unsigned long long)(A.tag_base | s);          // producer s-1 writes (s-1)+1
+        const unsigned long long myTag = (unsigned long long)(A.tag_base | (s + 1));
+        uint32_t *dbase = A.dirs + (size_t)s * A.strip_stride + lane;
+
+        // boundary-row prefetch: lanes 0..PB-1 hold the entries of one PB-column block
+        unsigned long long nextEnt = 0;
+        if (hasUp && lane < PB && lane < n) nextEnt = ld_volatile_u64(rowIn + lane);
+        int topBlk = 0;                                 // lane x: top value of column (blk*PB + x)
+        int letter = (lane == 0 && n > 0) ? min((int)A.text[0], alpha - 1) : 0;
+
+        for (int kb = 0; kb * CB < nSteps; ++kb) {
+            uint32_t acc[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) acc[w] = 0;
+#pragma unroll
+            for (int kk = 0; kk < CB; ++kk) {
+                const int k = kb * CB + kk;
+                const int jt = k - lane;
+                if ((k % PB) == 0 && k < n) {
+                    if (LOCAL) gmCached = max(gmCached, *reinterpret_cast<volatile int *>(A.gmax));
+                    // ---- take the prefetched block of the strip above, validating the tags ----
+                    if (hasUp) {
+                        unsigned long long cur = nextEnt;
+                        const int col = k + lane;
+                        const bool need = lane < PB && col < n;
+                        while (true) {
+                            const bool ok = !need || (cur >> 32) == wantTag;
+                            if (__all_sync(0xffffffffu, ok)) break;
+                            if (need && (cur >> 32) != wantTag) { __nanosleep(40); cur = ld_volatile_u64(rowIn + col); }
+                        }
+                        topBlk = (int)(uint32_t)cur;
+                        const int ncol = k + PB + lane;
+                        if (lane < PB && ncol < n) nextEnt = ld_volatile_u64(rowIn + ncol);
+                    } else {
+                        topBlk = LOCAL ? 0 : -SCALE * A.gap * (k + lane + 1 + (int)A.col0);
+                    }
+                }
+                const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
+                const int tv = __shfl_sync(0xffffffffu, topBlk, k % PB);
+                // text letter of the NEXT step, fetched one step ahead
+                const int curLetter = letter;
+                if (jt + 1 >= 0 && jt + 1 < n) letter = min((int)A.text[jt + 1], alpha - 1);
+                if (jt >= 0 && jt < n) {
+                    const int top = (lane == 0) ? tv : up;
+                    uint32_t prof[NPW];
+                    load_profile_words<R>(profS + curLetter * PS + lane * RPAD, prof);
+                    int bmax[nblk_for(R)];
+                    sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
+                    prevTop = top;
+                    bottom = c[R - 1];
+                    if (hasDown && lane == 31)
+                        st_volatile_u64(rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
+                    if (LOCAL) {
+                        const int colmax = max_of_blocks(bmax);
+                        if (row0 + lane * R < m &&
+                            track_argmax<R>(c, colmax, jt + 1 + (int)A.col0, snap, lane, gmCached, bestv, bestj) &&
+                            colmax > gmCached) {
+                            atomicMax(A.gmax, colmax);
+                            gmCached = colmax;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) dbase[(size_t)(kb * NW + w) * 32] = acc[w];
+        }
+
+        // ---- strip results ----
+        if (A.right_col) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int gi = row0 + lane * R + r + 1;
+                if (gi <= m) A.right_col[gi] = c[r];
+            }
+        }
+        if (LOCAL) {
+            besti = bestv > 0 ? row0 + lane * R + snapshot_first_row<R>(snap, lane, bestv) + 1 : 0;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+                const bool take = ov > bestv || (ov == bestv && (oi < besti || (oi == besti && oj < bestj)));
+                if (take) { bestv = ov; besti = oi; bestj = oj; }
+            }
+            if (lane == 0) { A.cand_v[s] = bestv; A.cand_i[s] = bestv > 0 ? besti : 0; A.cand_j[s] = bestv > 0 ? bestj : 0; }
+        } else {
+            const int lm = (m - 1 - row0) / R;
+            if (m - 1 >= row0 && m - 1 < row0 + ROWS && lane == lm) {
+                const int rm = (m - 1 - row0) % R;
+                int v = c[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) v = (r == rm) ? c[r] : v;
+                *A.score = v / SCALE;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Serial device traceback over the strip layout (one thread).  Same semantics as
+// batch_traceback_kernel; used for single long pairs.  Walks backwards writing into the END of
+// the output buffers (capacity cap), result offset = cap - len.
+struct LongTraceArgs {
+    const uint8_t *text;     uint32_t n;
+    const uint8_t *pattern;  uint32_t m;
+    const uint32_t *dirs;    uint64_t strip_stride;
+    const int32_t *S;  int alpha, gap, local;
+    int R, CB;
+    uint32_t n_strips;
+    const int *cand_v; const uint32_t *cand_i; const uint32_t *cand_j;
+    int32_t *score;          // in (NW) / out (SW)
+    char alphabet[MAX_ALPHA + 1];
+    uint64_t cap;
+    char *out_text; char *out_pattern;
+    uint64_t *res;           // [0]=len [1]=start_text [2]=start_pattern [3]=argmax linear index
+    int emit;                // 0: score / arg-max only (the reference's BENCHMARK mode)
+};
+
+__global__ void long_traceback_kernel(const LongTraceArgs A)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int NW = A.R * A.CB / 16;
+    const int ROWS = 32 * A.R;
+    const int n = (int)A.n, m = (int)A.m;
+    int i, j, H;
+    if (A.local) {
+        int bv = 0; uint32_t bi = 0, bj = 0;
+        for (uint32_t s = 0; s < A.n_strips; ++s) {
+            const int v = A.cand_v[s];
+            const uint32_t ci = A.cand_i[s], cj = A.cand_j[s];
+            if (v > bv || (v == bv && v > 0 && (ci < bi || (ci == bi && cj < bj)))) { bv = v; bi = ci; bj = cj; }
+        }
+        H = bv / SCALE; i = (int)bi; j = (int)bj;
+        *A.score = H;
+        A.res[3] = (uint64_t)i * (uint64_t)(n + 1) + (uint64_t)j;
+    } else {
+        H = *A.score; i = m; j = n;
+        A.res[3] = 0;
+    }
+    if (!A.emit) { A.res[0] = 0; A.res[1] = 0; A.res[2] = 0; return; }
+    const char GAPC = A.alphabet[A.alpha];
+    char *oT = A.out_text + A.cap, *oP = A.out_pattern + A.cap;
+    uint64_t len = 0;
+    size_t cachedAddr = ~(size_t)0; uint32_t cachedWord = 0;
+    auto fetch = [&](int ii, int jj) -> int {
+        const int s = (ii - 1) / ROWS, rr = (ii - 1) % ROWS;
+        const int ll = rr / A.R, r = rr % A.R;
+        const int k = (jj - 1) + ll;
+        const int kb = k / A.CB, kk = k % A.CB;
+        const int bit = (kk * A.R + r) * 2;
+        const size_t addr = (size_t)s * A.strip_stride + (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        if (addr != cachedAddr) { cachedAddr = addr; cachedWord = A.dirs[addr]; }
+        return (cachedWord >> (bit & 31)) & 3;
+    };
+    int ti, pi;
+    if (!A.local) {
+        ti = n - 1; pi = m - 1;
+        while (i > 0 || j > 0) {
+            int tag;
+            if (j == 0) tag = TAG_TOP;
+            else if (i == 0) tag = TAG_LEFT;
+            else tag = fetch(i, j);
+            const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
+            ++len;
+            oT[-(int64_t)len] = takeT ? A.alphabet[A.text[ti]] : GAPC;
+            oP[-(int64_t)len] = takeP ? A.alphabet[A.pattern[pi]] : GAPC;
+            ti = max(0, ti - (int)takeT);
+            pi = max(0, pi - (int)takeP);
+            i -= takeP; j -= takeT;
+        }
+    } else {
+        ti = j - 1; pi = i - 1;
+        while (H > 0) {
+            const int tag = fetch(i, j);
+            const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
+            ++len;
+            oT[-(int64_t)len] = takeT ? A.alphabet[A.text[ti]] : GAPC;
+            oP[-(int64_t)len] = takeP ? A.alphabet[A.pattern[pi]] : GAPC;
+            if (tag == TAG_DIAG) H -= A.S[A.pattern[i - 1] * A.alpha + A.text[j - 1]]; else H += A.gap;
+            i -= takeP; j -= takeT;
+            if (i == 0 || j == 0) break;
+            ti = max(0, ti - (int)takeT);
+            pi = max(0, pi - (int)takeP);
+        }
+    }
+    A.res[0] = len;
+    A.res[1] = (uint64_t)(int64_t)ti;
+    A.res[2] = (uint64_t)(int64_t)pi;
+}
+
+} // namespace sa

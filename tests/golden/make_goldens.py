@@ -133,9 +133,12 @@ def main():
         ("tests.cu:GPU_GLOBAL_PROTEIN_02", 0, 23, b50, 5, S["protein/P27895.fasta"], S["protein/P27895.fasta"], "tests/tests.cu:392-411", None),
     ]
     for name, mode, alpha, mat, gap, t, p, cite, exp in kat:
-        inline = len(t) <= 200
+        files = [next((k for k, v in S.items() if v is x), None) for x in (t, p)]
+        inline = None in files
         goldens.append(run(name, mode, alpha, mat, gap, t, p, cite, exp, keep=True, inline=inline,
                            matrix_name="dna/blast.txt" if alpha == 4 else "protein/blosum50.txt"))
+        if not inline:
+            goldens[-1]["files"] = files
 
     # ---- (b) BASELINE configs C1 / C2 ----
     goldens.append(run("C1:NC_018874xmutated NW blast g5", 0, 4, blast, 5, S["dna/NC_018874.txt"],

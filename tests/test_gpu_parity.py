@@ -1,0 +1,201 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(libsa_b200.so via ctypes), against the oracle and the committed reference goldens.
+Bit-exact: score, numAlignmentBytes, both start indices, both aligned strings."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from gpu_common import assert_same, load_package
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sa():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def aligner(sa):
+    a = sa.Aligner(0)
+    yield a
+    a.close()
+
+
+@pytest.fixture()
+def force_path(monkeypatch):
+    def _set(path=None, R=None):
+        for k, v in (("SA_FORCE_PATH", path), ("SA_LONG_R", R)):
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, str(v))
+    return _set
+
+
+def test_library_reports_device(sa):
+    assert sa.lib().sa_device_count() >= 1
+    assert b"sm_100a" in sa.lib().sa_version()
+
+
+def test_reference_known_answer_vectors(aligner):
+    """The reference's own golden vectors (tests/tests.cu:116-368)."""
+    n = 0
+    for g in helpers.goldens():
+        if not g["name"].startswith("tests.cu:"):
+            continue
+        t, p, mat = helpers.golden_inputs(g)
+        a = aligner.align(g["mode"], g["alpha"], mat, g["gap"], t, p)
+        helpers.check_against_golden(a, g)
+        n += 1
+    assert n >= 12
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_all_goldens_default_routing(aligner, chunk):
+    """Every committed reference output: data/ all-pairs sweep, C1/C2, matrices, synthetic, edges."""
+    gs = [g for g in helpers.goldens() if helpers.has_inputs(g)]
+    for g in gs[chunk::4]:
+        t, p, mat = helpers.golden_inputs(g)
+        a = aligner.align(g["mode"], g["alpha"], mat, g["gap"], t, p)
+        helpers.check_against_golden(a, g)
+
+
+@pytest.mark.parametrize("R", [4, 6, 8, 12, 16])
+def test_goldens_through_long_kernel(aligner, force_path, R):
+    """Short and medium goldens forced through the persistent strip kernel at every R."""
+    force_path("long", R)
+    gs = [g for g in helpers.goldens() if helpers.has_inputs(g) and g["n"] * g["m"] < 3e6]
+    for g in gs[R % 3::3]:
+        t, p, mat = helpers.golden_inputs(g)
+        a = aligner.align(g["mode"], g["alpha"], mat, g["gap"], t, p)
+        helpers.check_against_golden(a, g)
+
+
+@pytest.mark.parametrize("path", ["batch", "long"])
+@pytest.mark.parametrize("alpha", [4, 23])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_random_pairs_vs_oracle(aligner, oracle, force_path, path, alpha, mode):
+    force_path(path)
+    rng = np.random.default_rng(1000 + 10 * alpha + mode)
+    for it in range(120):
+        mat = rng.integers(-9, 12, (alpha, alpha)).astype(np.int32) if it % 3 == 0 else \
+            helpers.matrices()["dna/blast.txt" if alpha == 4 else "protein/blosum62.txt"]
+        nmax = [12, 70, 300, 1100][it % 4]
+        t, p = helpers.random_case(rng, alpha, n_max=nmax, similar=bool(it % 2))
+        gap = int(rng.integers(0, 12))
+        got = aligner.align(mode, alpha, mat, gap, t, p)
+        want = oracle.align(mode, alpha, mat, gap, t, p)
+        assert_same(got, want, (path, alpha, mode, it, gap, len(t), len(p)))
+
+
+def test_low_complexity_ties(aligner, oracle, force_path):
+    """Homopolymers / short repeats: every cell is a tie, arg-max has many candidates."""
+    mat = helpers.matrices()["dna/blast.txt"]
+    for path in ("batch", "long"):
+        force_path(path)
+        for mode in (0, 1):
+            for t, p in ((np.zeros(333, np.uint8), np.zeros(97, np.uint8)),
+                         (np.tile(np.arange(4, dtype=np.uint8), 90), np.tile(np.arange(4, dtype=np.uint8), 33)),
+                         (np.tile(np.array([0, 0, 1], np.uint8), 100), np.tile(np.array([0, 1], np.uint8), 60))):
+                for gap in (0, 1, 5):
+                    assert_same(aligner.align(mode, 4, mat, gap, t, p), oracle.align(mode, 4, mat, gap, t, p),
+                                (path, mode, gap, len(t)))
+
+
+def test_pattern_longer_than_text(aligner, oracle):
+    """Direct API callers may pass pattern > text (the reference would overflow its 2*text buffers)."""
+    rng = np.random.default_rng(5)
+    mat = helpers.matrices()["dna/blast.txt"]
+    t = rng.integers(0, 4, 50, dtype=np.uint8)
+    p = rng.integers(0, 4, 400, dtype=np.uint8)
+    for mode in (0, 1):
+        assert_same(aligner.align(mode, 4, mat, 5, t, p), oracle.align(mode, 4, mat, 5, t, p))
+
+
+def test_argument_errors(sa, aligner):
+    mat = helpers.matrices()["dna/blast.txt"]
+    with pytest.raises(sa.SaError):
+        aligner.align(0, 4, mat, 5, np.zeros(0, np.uint8), np.zeros(3, np.uint8))
+    with pytest.raises(sa.SaError):
+        aligner.align(0, 4, np.full(16, 1000, np.int32), 5, np.zeros(3, np.uint8), np.zeros(3, np.uint8))
+
+
+def test_host_batch_vs_oracle(sa, aligner, oracle):
+    rng = np.random.default_rng(77)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    for mode in (0, 1):
+        texts, pats = [], []
+        for i in range(700):
+            t, p = helpers.random_case(rng, 23, n_max=[40, 180, 350][i % 3], similar=bool(i % 2))
+            texts.append(t)
+            pats.append(p)
+        toff = np.concatenate(([0], np.cumsum([len(t) for t in texts]))).astype(np.int64)
+        poff = np.concatenate(([0], np.cumsum([len(p) for p in pats]))).astype(np.int64)
+        out = aligner.align_batch(mode, 23, mat, 5, np.concatenate(texts), toff, np.concatenate(pats), poff)
+        for i in range(len(texts)):
+            assert_same(sa.unpack_batch(out, i), oracle.align(mode, 23, mat, 5, texts[i], pats[i]), (mode, i))
+
+
+def test_host_batch_with_long_members(sa, aligner, oracle):
+    """A batch that mixes short pairs with pairs too long for the batch kernel."""
+    rng = np.random.default_rng(78)
+    mat = helpers.matrices()["dna/blast.txt"]
+    texts, pats = [], []
+    for nmax in (50, 3000, 200, 700, 9):
+        t, p = helpers.random_case(rng, 4, n_max=nmax)
+        texts.append(t)
+        pats.append(p)
+    toff = np.concatenate(([0], np.cumsum([len(t) for t in texts]))).astype(np.int64)
+    poff = np.concatenate(([0], np.cumsum([len(p) for p in pats]))).astype(np.int64)
+    for mode in (0, 1):
+        out = aligner.align_batch(mode, 4, mat, 5, np.concatenate(texts), toff, np.concatenate(pats), poff)
+        for i in range(len(texts)):
+            assert_same(sa.unpack_batch(out, i), oracle.align(mode, 4, mat, 5, texts[i], pats[i]), (mode, i))
+
+
+def test_device_batch_torch_tensors(sa, aligner, oracle):
+    """sa_align_batch_device on torch tensors / torch's current stream (the bench's `value` path)."""
+    import torch
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(3000, seed=9, lo=250, hi=350)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    dev = torch.device("cuda:0")
+    dT, dP = torch.from_numpy(T).to(dev), torch.from_numpy(P).to(dev)
+    dto, dpo = torch.from_numpy(toff).to(dev), torch.from_numpy(poff).to(dev)
+    N = len(toff) - 1
+    arena = int(toff[-1] + poff[-1])
+    res = torch.zeros(N * 4, dtype=torch.int64, device=dev)
+    aoff = torch.zeros(N, dtype=torch.int64, device=dev)
+    oT = torch.zeros(arena, dtype=torch.uint8, device=dev)
+    oP = torch.zeros(arena, dtype=torch.uint8, device=dev)
+    max_n = int((toff[1:] - toff[:-1]).max())
+    max_m = int((poff[1:] - poff[:-1]).max())
+    for mode in (1, 0):
+        aligner.align_batch_device(mode, 23, mat, 5, N, dT.data_ptr(), dto.data_ptr(), dP.data_ptr(), dpo.data_ptr(),
+                                   res.data_ptr(), aoff.data_ptr(), oT.data_ptr(), oP.data_ptr(), arena, max_n, max_m,
+                                   stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        out = dict(results=res.cpu().numpy().view(sa.RESULT_DTYPE), aln_off=aoff.cpu().numpy().astype(np.uint64),
+                   aligned_text=oT.cpu().numpy(), aligned_pattern=oP.cpu().numpy())
+        for i in range(0, N, 7):
+            t, p = T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]
+            assert_same(sa.unpack_batch(out, i), oracle.align(mode, 23, mat, 5, t, p), (mode, i))
+
+
+def test_reference_operator_interface(sa):
+    """Request / Response / alignSequenceGPU mirror SequenceAlignment.hpp:71-131."""
+    g = next(x for x in helpers.goldens() if x["name"] == "tests.cu:LOCAL_DNA_01")
+    t, p, mat = helpers.golden_inputs(g)
+    rq = sa.Request(deviceType=sa.programArgs.GPU, sequenceType=sa.programArgs.DNA, alignmentType=sa.programArgs.LOCAL,
+                    textBytes=t, textNumBytes=len(t), patternBytes=p, patternNumBytes=len(p), alphabet=sa.DNA_ALPHABET,
+                    alphabetSize=4, gapPenalty=5)
+    rq.scoreMatrix[:16] = mat
+    rs = sa.Response()
+    assert sa.alignSequenceGPU(rq, rs) == 0
+    assert (rs.score, rs.alignedTextBytes, rs.alignedPatternBytes) == (20, b"ACAC", b"ACAC")
+    assert (rs.startInAlignedText, rs.startInAlignedPattern, rs.numAlignmentBytes) == (248, 0, 4)
+    rq.alignmentType = sa.programArgs.SEMI_GLOBAL       # declared, never implemented: silent no-op
+    assert sa.alignSequenceGPU(rq, sa.Response()) == 0

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Dev tool: time the batch fill / traceback kernels for several (R, L) configurations.
+usage: python tools/sweep_batch.py [pairs] [cfg ...]   e.g. 100000 24,16 48,8 12,32"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sequence-alignment-gpu_b200"))
+from __graft_entry__ import load_package  # noqa: E402
+import synth  # noqa: E402
+import json
+
+sa = load_package()
+pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+cfgs = sys.argv[2:] or ["24,16", "48,8", "12,32"]
+mode = int(os.environ.get("SWEEP_MODE", "1"))
+T, toff, P, poff = synth.synthetic_batch(pairs, seed=2024)
+mat = np.asarray(json.load(open(os.path.join(ROOT, "tests/golden/matrices.json")))["protein/blosum62.txt"], np.int32)
+dev = torch.device("cuda:0")
+dT, dP = torch.from_numpy(T).to(dev), torch.from_numpy(P).to(dev)
+dto, dpo = torch.from_numpy(toff).to(dev), torch.from_numpy(poff).to(dev)
+N = pairs
+arena = int(toff[-1] + poff[-1])
+res = torch.zeros(N * 4, dtype=torch.int64, device=dev)
+aoff = torch.zeros(N, dtype=torch.int64, device=dev)
+oT = torch.zeros(arena, dtype=torch.uint8, device=dev)
+oP = torch.zeros(arena, dtype=torch.uint8, device=dev)
+max_n = int((toff[1:] - toff[:-1]).max())
+max_m = int((poff[1:] - poff[:-1]).max())
+cells = float(((toff[1:] - toff[:-1] + 1) * (poff[1:] - poff[:-1] + 1)).sum())
+al = sa.Aligner(0)
+ref = None
+for cfg in cfgs:
+    os.environ["SA_BATCH_CLASSES"] = cfg
+    best = None
+    for it in range(4):
+        al.align_batch_device(mode, 23, mat, 5, N, dT.data_ptr(), dto.data_ptr(), dP.data_ptr(), dpo.data_ptr(),
+                              res.data_ptr(), aoff.data_ptr(), oT.data_ptr(), oP.data_ptr(), arena, max_n, max_m,
+                              stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        t = al.timing()
+        if it and (best is None or t["fill_us"] < best["fill_us"]):
+            best = t
+    chk = int(res.view(-1, 4)[:, 0].sum().item())
+    ref = ref if ref is not None else chk
+    print(f"cfg {cfg:>6s}: fill {best['fill_us']/1e3:8.3f} ms  {cells/best['fill_us']/1e3:8.1f} GCUPS | traceback {best['traceback_us']/1e3:7.3f} ms"
+          f" | checksum {'ok' if chk == ref else 'MISMATCH'}", flush=True)

@@ -5,6 +5,7 @@
 #include "../../include/sa_b200.h"
 #include "sa_batch.cuh"
 #include "sa_long.cuh"
+#include "sa_traceback.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -72,7 +73,7 @@ struct sa_context {
     // scoring tables on the device
     DevBuf dS4, dS;
     // single-pair / device-batch workspaces
-    DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf;
+    DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf, tbbuf;
     PinBuf pin;
     Slot slot[NSLOT];
     uint32_t epoch = 0;
@@ -331,7 +332,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
 
 // ------------------------------------------------------------------ long-pair dispatch
 constexpr int LONG_WARPS = 4;
-const int kLongR[] = {4, 6, 8, 12, 16};
+const int kLongR[] = {2, 4, 6, 8, 12, 16};
 
 template <int R>
 cudaError_t launch_long_t(const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
@@ -354,6 +355,7 @@ int occupancy_long_t(bool local, size_t smem)
 }
 #define LONG_DISPATCH(FN, ...)                       \
     switch (R) {                                     \
+    case 2: return FN<2>(__VA_ARGS__);               \
     case 4: return FN<4>(__VA_ARGS__);               \
     case 6: return FN<6>(__VA_ARGS__);               \
     case 8: return FN<8>(__VA_ARGS__);               \
@@ -390,7 +392,7 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
     }
     P->R = R; P->CB = cb_for(R); P->NW = R * P->CB / 16;
     P->n_strips = (uint32_t)((m + 32ull * R - 1) / (32ull * R));
-    P->smem = 32 * MAX_ALPHA + (size_t)LONG_WARPS * ((size_t)sc->alphabet_size * 32 * rpad_for(R) + (local ? ((R + 3) / 4) * 32 * 16 : 0));
+    P->smem = 32 * MAX_ALPHA + (size_t)LONG_WARPS * ((size_t)sc->alphabet_size * 32 * rpad_for(R) + (local ? ((R + 3) / 4) * 32 * 16 : 0) + 64 + 2 * PB * 4);
     int occ = occupancy_long(R, local, P->smem);
     if (occ < 1) return SA_ERR_LAUNCH;
     const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
@@ -449,19 +451,71 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
     cudaEventRecord(e1, st);
     ctx->timing.kernel_launches++;
 
-    LongTraceArgs T{};
-    T.text = d_text; T.n = (uint32_t)n; T.pattern = d_pat; T.m = (uint32_t)m;
-    T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = P.strip_stride;
-    T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
-    T.R = P.R; T.CB = P.CB; T.n_strips = P.n_strips;
-    T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
-    std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
-    T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
-    T.emit = traceback ? 1 : 0;
-    long_traceback_kernel<<<1, 32, 0, st>>>(T);
-    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    const char *tbmode = std::getenv("SA_TB");
+    if (tbmode && !std::strcmp(tbmode, "serial")) {
+        // reference implementation of the device traceback: one thread chasing pointers
+        LongTraceArgs T{};
+        T.text = d_text; T.n = (uint32_t)n; T.pattern = d_pat; T.m = (uint32_t)m;
+        T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = P.strip_stride;
+        T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
+        T.R = P.R; T.CB = P.CB; T.n_strips = P.n_strips;
+        T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
+        std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
+        T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
+        T.emit = traceback ? 1 : 0;
+        long_traceback_kernel<<<1, 32, 0, st>>>(T);
+        SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+        ctx->timing.kernel_launches++;
+    } else {
+        // parallel traceback (sa_traceback.cuh): walkers -> resolve -> count -> offsets -> emit
+        TbArgs T{};
+        T.Lay.dirs = ctx->dirs.as<uint32_t>(); T.Lay.strip_stride = P.strip_stride;
+        T.Lay.R = P.R; T.Lay.CB = P.CB; T.Lay.NW = P.NW; T.Lay.ROWS = 32 * P.R; T.Lay.n = (int)n; T.Lay.m = (int)m;
+        T.text = d_text; T.pattern = d_pat;
+        T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
+        T.n_strips = P.n_strips;
+        int Wd = 16;
+        while (Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;          // power of two <= ROWS/2
+        if (const char *e = std::getenv("SA_TB_WD")) { const int w = std::atoi(e); if (w >= 1) Wd = w; }
+        T.Wd = Wd; T.Q = (int)((n + Wd - 1) / Wd);
+        {
+            // band of candidates around the predicted crossing: +-max(2048 columns, n/50)
+            const uint64_t half = std::max<uint64_t>(2048, n / 50);
+            int bq = (int)((half + Wd - 1) / Wd);
+            if (const char *e = std::getenv("SA_TB_BAND")) { const int b = std::atoi(e); if (b >= 1) bq = b; }
+            T.BQ = std::max(1, std::min(bq, std::max(1, T.Q / 2)));
+            T.slope = local ? 1.0 : (double)n / (double)m;
+        }
+        T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
+        const size_t nq = (size_t)2 * T.BQ + 1, S = P.n_strips;
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t oSt = carve(sizeof(TbState)), oX = carve((S + 1) * 4), oLen = carve(S * 8), oDel = carve(S * 8),
+                     oMin = carve(S * 8), oOff = carve(S * 8), oFa = carve(S * nq * 4);
+        SA_TRY(ctx->tbbuf.reserve(off), SA_ERR_MEMORY);
+        char *base = ctx->tbbuf.as<char>();
+        T.st = reinterpret_cast<TbState *>(base + oSt); T.X = reinterpret_cast<int *>(base + oX);
+        T.seg_len = reinterpret_cast<unsigned long long *>(base + oLen);
+        T.seg_delta = reinterpret_cast<long long *>(base + oDel); T.seg_min = reinterpret_cast<long long *>(base + oMin);
+        T.seg_off = reinterpret_cast<unsigned long long *>(base + oOff); T.fa = reinterpret_cast<uint32_t *>(base + oFa);
+        std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
+        T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
+        tb_prepare_kernel<<<1, 32, 0, st>>>(T);
+        ctx->timing.kernel_launches++;
+        if (traceback) {
+            const long long walkers = (long long)S * (long long)nq;
+            tb_walkers_kernel<<<(unsigned)((walkers + 127) / 128), 128, 0, st>>>(T);
+            tb_resolve_kernel<<<1, 32, 0, st>>>(T);
+            tb_count_kernel<<<(unsigned)((S + 63) / 64), 64, 0, st>>>(T);
+            tb_offsets_kernel<<<1, 32, 0, st>>>(T);
+            tb_emit_kernel<<<(unsigned)((S + 63) / 64), 64, 0, st>>>(T);
+            ctx->timing.kernel_launches += 5;
+        } else {
+            SA_TRY(cudaMemsetAsync(d_res, 0, 24, st), SA_ERR_LAUNCH);
+        }
+        SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    }
     cudaEventRecord(e2, st);
-    ctx->timing.kernel_launches++;
     ctx->timing_dirty = true;
     return SA_OK;
 }
@@ -537,7 +591,7 @@ void sa_destroy(sa_context *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf})
+    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf, &ctx->tbbuf})
         b->release();
     ctx->pin.release();
     for (auto &s : ctx->slot) {

@@ -15,6 +15,7 @@
 //     word(s, kb, w, lane) at s*stripStride + (kb*NW + w)*32 + lane,   kb = step / CB.
 #pragma once
 #include "sa_cell.cuh"
+#include <type_traits>
 
 namespace sa {
 
@@ -67,8 +68,11 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
     const int alpha = A.alpha;
     int8_t *S4s = reinterpret_cast<int8_t *>(smem);
     constexpr uint32_t snapBytes = LOCAL ? ((R + 3) / 4) * 32 * 16 : 0;
-    unsigned char *profS = smem + 32 * MAX_ALPHA + (size_t)warp * (alpha * PS + snapBytes);
+    constexpr uint32_t winBytes = 64 + 2 * PB * 4;                     // text window + top-row window
+    unsigned char *profS = smem + 32 * MAX_ALPHA + (size_t)warp * (alpha * PS + snapBytes + winBytes);
     uint4 *snap = reinterpret_cast<uint4 *>(profS + alpha * PS);
+    unsigned char *textWin = profS + alpha * PS + snapBytes;
+    int *topWin = reinterpret_cast<int *>(textWin + 64);
     for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
     __syncthreads();
 
@@ -117,67 +121,116 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         const unsigned long long myTag = (unsigned long long)(A.tag_base | (s + 1));
         uint32_t *dbase = A.dirs + (size_t)s * A.strip_stride + lane;
 
-        // boundary-row prefetch: lanes 0..PB-1 hold the entries of one PB-column block
+        // Everything a step needs besides `up` is fetched ONE STEP AHEAD (text letter -> profile words,
+        // lane 0's top value), so the per-step critical path is just SHFL.UP -> R cells.
+        //   textWin : 64-byte window of the text (two 32-letter blocks), refilled every 32 steps
+        //   topWin  : 2*PB top-row values of the strip above (validated {value, tag} words)
+        __syncwarp();
+        if (lane < n) textWin[lane] = (unsigned char)min((int)A.text[lane], alpha - 1);
+        int tnext = (32 + lane < n) ? min((int)A.text[32 + lane], alpha - 1) : 0;    // block 1, stored at step 31
         unsigned long long nextEnt = 0;
-        if (hasUp && lane < PB && lane < n) nextEnt = ld_volatile_u64(rowIn + lane);
-        int topBlk = 0;                                 // lane x: top value of column (blk*PB + x)
-        int letter = (lane == 0 && n > 0) ? min((int)A.text[0], alpha - 1) : 0;
-
-        for (int kb = 0; kb * CB < nSteps; ++kb) {
-            uint32_t acc[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) acc[w] = 0;
-#pragma unroll
-            for (int kk = 0; kk < CB; ++kk) {
-                const int k = kb * CB + kk;
-                const int jt = k - lane;
-                if ((k % PB) == 0 && k < n) {
-                    if (LOCAL) gmCached = max(gmCached, *reinterpret_cast<volatile int *>(A.gmax));
-                    // ---- take the prefetched block of the strip above, validating the tags ----
-                    if (hasUp) {
-                        unsigned long long cur = nextEnt;
-                        const int col = k + lane;
-                        const bool need = lane < PB && col < n;
-                        while (true) {
-                            const bool ok = !need || (cur >> 32) == wantTag;
-                            if (__all_sync(0xffffffffu, ok)) break;
-                            if (need && (cur >> 32) != wantTag) { __nanosleep(40); cur = ld_volatile_u64(rowIn + col); }
-                        }
-                        topBlk = (int)(uint32_t)cur;
-                        const int ncol = k + PB + lane;
-                        if (lane < PB && ncol < n) nextEnt = ld_volatile_u64(rowIn + ncol);
-                    } else {
-                        topBlk = LOCAL ? 0 : -SCALE * A.gap * (k + lane + 1 + (int)A.col0);
-                    }
+        // Top-row blocks are requested FOUR blocks (32 columns) ahead so that the L2 round trip of the
+        // tagged words never sits on the critical path: lanes 8g..8g+7 own the blocks b with b%4 == g.
+        auto take_top_block = [&](const int blk) {
+            const bool mine = (lane >> 3) == (blk & 3);
+            const int col = blk * PB + (lane & 7);
+            const bool need = mine && col < n;
+            if (hasUp) {
+                unsigned long long cur = nextEnt;
+                while (true) {
+                    const bool ok = !need || (cur >> 32) == wantTag;
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (need && (cur >> 32) != wantTag) { __nanosleep(20); cur = ld_volatile_u64(rowIn + col); }
                 }
-                const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
-                const int tv = __shfl_sync(0xffffffffu, topBlk, k % PB);
-                // text letter of the NEXT step, fetched one step ahead
-                const int curLetter = letter;
-                if (jt + 1 >= 0 && jt + 1 < n) letter = min((int)A.text[jt + 1], alpha - 1);
-                if (jt >= 0 && jt < n) {
-                    const int top = (lane == 0) ? tv : up;
-                    uint32_t prof[NPW];
-                    load_profile_words<R>(profS + curLetter * PS + lane * RPAD, prof);
-                    int bmax[nblk_for(R)];
-                    sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
-                    prevTop = top;
-                    bottom = c[R - 1];
-                    if (hasDown && lane == 31)
-                        st_volatile_u64(rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
-                    if (LOCAL) {
-                        const int colmax = max_of_blocks(bmax);
-                        if (row0 + lane * R < m &&
-                            track_argmax<R>(c, colmax, jt + 1 + (int)A.col0, snap, lane, gmCached, bestv, bestj) &&
-                            colmax > gmCached) {
-                            atomicMax(A.gmax, colmax);
-                            gmCached = colmax;
-                        }
+                if (need) topWin[(blk & 1) * PB + (lane & 7)] = (int)(uint32_t)cur;
+                const int ncol = col + 4 * PB;
+                if (mine && ncol < n) nextEnt = ld_volatile_u64(rowIn + ncol);
+            } else if (need) {
+                topWin[(blk & 1) * PB + (lane & 7)] = LOCAL ? 0 : -SCALE * A.gap * (col + 1 + (int)A.col0);
+            }
+        };
+        // window upkeep that must precede the prefetch for step k1 (= k+1)
+        auto upkeep = [&](const int k1) {
+            if ((k1 & 31) == 0) {
+                textWin[((k1 >> 5) & 1) * 32 + lane] = (unsigned char)tnext;
+                const int tcol = k1 + 32 + lane;
+                tnext = tcol < n ? min((int)A.text[tcol], alpha - 1) : 0;
+                if (LOCAL) gmCached = max(gmCached, *reinterpret_cast<volatile int *>(A.gmax));
+            }
+            if ((k1 % PB) == 0) {
+                if (k1 < n) take_top_block(k1 / PB);
+                __syncwarp();
+            }
+        };
+        if (hasUp && lane < n) nextEnt = ld_volatile_u64(rowIn + lane);      // blocks 0..3
+        take_top_block(0);
+        __syncwarp();
+        uint32_t profN[NPW];
+#pragma unroll
+        for (int q = 0; q < NPW; ++q) profN[q] = 0;
+        if (lane == 0 && n > 0) load_profile_words<R>(profS + (int)textWin[0] * PS, profN);
+        int topN = topWin[0];
+        uint32_t acc[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) acc[w] = 0;
+
+        // One wavefront step.  FAST = steady state (every lane has a column, upkeep done by the caller).
+        auto step = [&](const int k, const int kk, auto fastTag) {
+            constexpr bool FAST = decltype(fastTag)::value;
+            const int jt = k - lane, k1 = k + 1, jn = k1 - lane;
+            uint32_t prof[NPW];
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) prof[q] = profN[q];
+            const int topv = topN;
+            if (!FAST) upkeep(k1);
+            // next step's letter first: its shared-memory latency hides behind the sweep below
+            const bool nextActive = FAST || (jn >= 0 && jn < n);
+            const int letterN = nextActive ? (int)textWin[jn & 63] : 0;
+            topN = topWin[k1 & (2 * PB - 1)];
+            const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
+            if (FAST || (jt >= 0 && jt < n)) {
+                const int top = (lane == 0) ? topv : up;
+                int bmax[nblk_for(R)];
+                sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
+                prevTop = top;
+                bottom = c[R - 1];
+                if (hasDown && lane == 31)
+                    st_volatile_u64(rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
+                if (LOCAL) {
+                    const int colmax = max_of_blocks(bmax);
+                    if (row0 + lane * R < m &&
+                        track_argmax<R>(c, colmax, jt + 1 + (int)A.col0, snap, lane, gmCached, bestv, bestj) &&
+                        colmax > gmCached) {
+                        atomicMax(A.gmax, colmax);
+                        gmCached = colmax;
                     }
                 }
             }
+            if (nextActive) load_profile_words<R>(profS + letterN * PS + lane * RPAD, profN);
+            if (kk == CB - 1) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) dbase[(size_t)(kb * NW + w) * 32] = acc[w];
+                for (int w = 0; w < NW; ++w) { dbase[(size_t)((k / CB) * NW + w) * 32] = acc[w]; acc[w] = 0; }
+            }
+        };
+
+        // ramp-up (k < 32), steady state in sub-blocks of 8 steps, drain
+        const int kFast0 = 32, kFast1 = (n >= 64) ? (n / 32) * 32 : 32;
+        const int nStepsPad = (nSteps + CB - 1) / CB * CB;
+        int k = 0;
+        for (; k < min(kFast0, nStepsPad); k += CB) {
+#pragma unroll
+            for (int kk = 0; kk < CB; ++kk) step(k + kk, kk, std::false_type{});
+        }
+        for (; k < kFast1; k += 8) {
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+                if (k8 == 7) upkeep(k + 8);
+                step(k + k8, k8 % CB, std::true_type{});
+            }
+        }
+        for (; k < nStepsPad; k += CB) {
+#pragma unroll
+            for (int kk = 0; kk < CB; ++kk) step(k + kk, kk, std::false_type{});
         }
 
         // ---- strip results ----

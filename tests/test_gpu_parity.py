@@ -63,7 +63,7 @@ def test_all_goldens_default_routing(aligner, chunk):
         helpers.check_against_golden(a, g)
 
 
-@pytest.mark.parametrize("R", [4, 6, 8, 12, 16])
+@pytest.mark.parametrize("R", [2, 4, 6, 8, 12, 16])
 def test_goldens_through_long_kernel(aligner, force_path, R):
     """Short and medium goldens forced through the persistent strip kernel at every R."""
     force_path("long", R)
@@ -199,3 +199,27 @@ def test_reference_operator_interface(sa):
     assert (rs.startInAlignedText, rs.startInAlignedPattern, rs.numAlignmentBytes) == (248, 0, 4)
     rq.alignmentType = sa.programArgs.SEMI_GLOBAL       # declared, never implemented: silent no-op
     assert sa.alignSequenceGPU(rq, sa.Response()) == 0
+
+
+@pytest.mark.parametrize("variant", [dict(SA_TB="serial"), dict(SA_TB_WD="16"), dict(SA_TB_WD="200"), dict(SA_LONG_R="4", SA_TB_WD="32"), dict(SA_TB_BAND="1"), dict(SA_LONG_R="2")])
+def test_long_traceback_variants(aligner, oracle, force_path, monkeypatch, variant):
+    """Parallel traceback (walkers / resolve / segments) vs the serial device walk vs the oracle,
+    with candidate spacings that force both the merged-bracket and the fallback paths."""
+    force_path("long")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(4242)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+    cases = []
+    for it in range(10):
+        alpha, mat = (4, blast) if it % 2 == 0 else (23, b62)
+        t, p = helpers.random_case(rng, alpha, n_max=[400, 2500, 6000][it % 3], similar=it % 4 != 3)
+        cases.append((alpha, mat, t, p))
+    # dissimilar sequences: paths meander, brackets often disagree -> serial fallback segments
+    cases.append((4, blast, rng.integers(0, 4, 3000, dtype=np.uint8), rng.integers(0, 4, 2500, dtype=np.uint8)))
+    for alpha, mat, t, p in cases:
+        for mode in (0, 1):
+            for gap in (2, 7):
+                assert_same(aligner.align(mode, alpha, mat, gap, t, p), oracle.align(mode, alpha, mat, gap, t, p),
+                            (variant, alpha, mode, gap, len(t), len(p)))

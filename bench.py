@@ -246,7 +246,9 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     al = sa.Aligner(local_rank)
     w = make_workload(args, rank)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)           # the kernels are launched (and timed) on this stream
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     pk = peaks()
 
     def barrier():

@@ -93,6 +93,8 @@ int sa_last_timing(const sa_context *ctx, sa_timing *out);
 /* cudaError_t of the last failing CUDA call on this context (0 if none): the reference
  * swallows these (no cudaGetLastError after launches, alignSequenceGPU.cu:575-611). */
 int sa_last_cuda_error(const sa_context *ctx);
+/* The context's own (non-blocking) cudaStream_t, used by the host-buffer entry points. */
+void *sa_context_stream(const sa_context *ctx);
 
 /* ---- single pair: replaces alignSequenceGPU (alignSequenceGPU.cu:463-653) ---
  * HOST buffers in, HOST buffers out.  aligned_text / aligned_pattern must hold
@@ -150,8 +152,8 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *scoring,
 
 /* DEVICE-resident variant: every pointer in `batch` and `out` is a device
  * pointer (e.g. torch tensors' data_ptr()), work is enqueued on `stream`
- * (a cudaStream_t; 0 = the context's own stream) and the call returns without
- * synchronising.  max_text_len / max_pattern_len bound the pair sizes (they
+ * (a cudaStream_t used as given; NULL is the CUDA default stream) and the call
+ * returns without synchronising.  max_text_len / max_pattern_len bound the pair sizes (they
  * size the direction workspace). */
 int sa_align_batch_device(sa_context *ctx, const sa_scoring *scoring,
                           const sa_batch *batch, sa_batch_out *out,

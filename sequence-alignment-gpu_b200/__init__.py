@@ -114,6 +114,8 @@ def lib() -> C.CDLL:
         L.sa_destroy.argtypes = [C.c_void_p]
         L.sa_last_timing.argtypes = [C.c_void_p, C.POINTER(_Timing)]
         L.sa_last_cuda_error.argtypes = [C.c_void_p]
+        L.sa_context_stream.restype = C.c_void_p
+        L.sa_context_stream.argtypes = [C.c_void_p]
         L.sa_align.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                C.POINTER(_Result), C.c_void_p, C.c_void_p, C.c_uint64]
         L.sa_fill_only.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,

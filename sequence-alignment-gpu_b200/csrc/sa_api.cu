@@ -627,6 +627,8 @@ int sa_last_timing(const sa_context *cctx, sa_timing *out)
 
 int sa_last_cuda_error(const sa_context *ctx) { return ctx ? ctx->last_cuda : 0; }
 
+void *sa_context_stream(const sa_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 // --------------------------------------------------------------- single pair
 static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *text, uint64_t n,
                         const uint8_t *pattern, uint64_t m, sa_result *result, char *outT, char *outP,
@@ -749,7 +751,7 @@ int sa_align_device(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text
     if (!ctx || !sc || !d_text || !d_pattern || !d_outT || !d_outP || !d_result4 || n == 0 || m == 0) return SA_ERR_ARGUMENT;
     if (n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // as given; NULL is the CUDA default stream
     int rc = upload_scoring(ctx, sc, st);
     if (rc) return rc;
     reset_timing(ctx);
@@ -772,7 +774,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     if (b->n_pairs == 0) return SA_OK;
     if (b->n_pairs >= (1ull << 31)) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // as given; NULL is the CUDA default stream
     int rc = upload_scoring(ctx, sc, st);
     if (rc) return rc;
     BatchClassTable T;

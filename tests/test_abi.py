@@ -78,3 +78,28 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "sa_oracle" not in src and "oracle_py" not in src and "libsa_ref" not in src, f
+
+
+def test_reference_driver_links_against_the_library(sa, tmp_path):
+    """INTEGRATION.md recipe: the reference's own mainDriver.cu, built with the one-line header change
+    (unity include of alignSequenceGPU.cu removed), links against libsa_b200.so and its CPU path still
+    answers the reference's golden case.  Needs the reference tree (build container only)."""
+    import shutil
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "mainDriver.cu")) or shutil.which("nvcc") is None:
+        pytest.skip("reference tree / nvcc not available")
+    for f in ("mainDriver.cu", "SequenceAlignment.hpp", "utilities.cpp", "alignSequenceCPU.cpp"):
+        shutil.copy(os.path.join(ref, f), tmp_path / f)          # scratch copy, never committed
+    hdr = (tmp_path / "SequenceAlignment.hpp").read_text()
+    assert '#include "alignSequenceGPU.cu"' in hdr
+    (tmp_path / "SequenceAlignment.hpp").write_text(hdr.replace('#include "alignSequenceGPU.cu"', ""))
+    libdir = os.path.dirname(sa.LIB_PATH)
+    exe = tmp_path / "alignSequence"
+    r = subprocess.run(["nvcc", "-std=c++14", "-m64", "--expt-relaxed-constexpr", "-include", "cstdint", "-w",
+                        str(tmp_path / "mainDriver.cu"), "-o", str(exe), f"-L{libdir}", "-lsa_b200",
+                        f"-Xlinker=-rpath={libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe), "-c", "--global", "data/dna/dna_01.txt", "data/dna/dna_02.txt"], cwd=ref,
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and "# Score: \t-4" in out.stdout, out.stdout + out.stderr

@@ -173,6 +173,8 @@ def test_device_batch_torch_tensors(sa, aligner, oracle):
     oP = torch.zeros(arena, dtype=torch.uint8, device=dev)
     max_n = int((toff[1:] - toff[:-1]).max())
     max_m = int((poff[1:] - poff[:-1]).max())
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
     for mode in (1, 0):
         aligner.align_batch_device(mode, 23, mat, 5, N, dT.data_ptr(), dto.data_ptr(), dP.data_ptr(), dpo.data_ptr(),
                                    res.data_ptr(), aoff.data_ptr(), oT.data_ptr(), oP.data_ptr(), arena, max_n, max_m,

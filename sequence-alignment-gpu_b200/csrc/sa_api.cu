@@ -58,7 +58,7 @@ constexpr int NSLOT = 3;   // pipeline depth of the host batch path
 
 struct Slot {              // per-chunk device buffers of the host batch path
     cudaStream_t stream = nullptr;
-    DevBuf text, pattern, toff, poff, results, alnoff, outT, outP, dirs, fill, order;
+    DevBuf text, pattern, toff, poff, results, alnoff, outT, outP, dirs, fill, order, snap;
     cudaEvent_t done = nullptr;
 };
 
@@ -73,7 +73,10 @@ struct sa_context {
     // scoring tables on the device
     DevBuf dS4, dS;
     // single-pair / device-batch workspaces
-    DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf, tbbuf;
+    DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf, tbbuf, snapbuf;
+    // device-batch pipeline: fills on the caller's stream, tracebacks on `stream`, two buffer sets
+    DevBuf pdirs[2], psort[2];
+    cudaEvent_t evFill[2] = {}, evTrace[2] = {};
     PinBuf pin;
     Slot slot[NSLOT];
     uint32_t epoch = 0;
@@ -84,7 +87,7 @@ struct sa_context {
     size_t evused = 0;
     bool timing_dirty = false;
     int last_cuda = 0;
-    size_t dirs_budget = (size_t)6 << 30;   // bytes of direction workspace per chunk
+    size_t dirs_budget = (size_t)8 << 30;   // bytes of direction workspace per chunk
 };
 
 namespace {
@@ -149,7 +152,10 @@ const BatchCfg kBatchCfgs[] = {{8, 16}, {12, 16}, {16, 16}, {20, 16}, {24, 16}, 
 // every instantiation of batch_fill_kernel
 #define SA_BATCH_CFG_LIST(X) X(8, 8) X(16, 8) X(32, 8) X(40, 8) X(48, 8) X(8, 16) X(12, 16) X(16, 16) X(20, 16) X(24, 16) \
     X(8, 32) X(10, 32) X(12, 32) X(16, 32) X(24, 32) X(32, 32) X(48, 32)
-constexpr int BATCH_WARPS = 4;   // warps per block
+#ifndef SA_BATCH_WARPS
+#define SA_BATCH_WARPS 4
+#endif
+constexpr int BATCH_WARPS = SA_BATCH_WARPS;   // warps per block
 constexpr uint32_t BATCH_MAX_TEXT = 16384;
 constexpr uint32_t BATCH_MAX_ROWS = 1536;
 
@@ -172,7 +178,7 @@ size_t batch_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n, bool local
 {
     const int G = 32 / c.L;
     const size_t group = ((size_t)alpha * c.L * rpad_for(c.R) + ((max_n + 15u) & ~15u) + 15u) & ~(size_t)15;
-    const size_t snap = local ? (size_t)((c.R + 3) / 4) * 32 * 16 + 16 * G : 0;
+    const size_t snap = local ? (size_t)16 * G : 0;
     return 32 * MAX_ALPHA + (size_t)BATCH_WARPS * (G * group + snap);
 }
 
@@ -266,9 +272,11 @@ int occupancy_batch(const BatchCfg &cfg, bool local, size_t smem)
 // them one by one through the long-pair kernels).
 int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_result *d_results,
                   uint64_t *d_alnoff, char *d_outT, char *d_outP, uint32_t max_n, uint32_t max_m,
-                  uint32_t *d_dirs, size_t dirs_words, void *d_fill, void *d_sort, cudaStream_t st,
-                  uint32_t first, uint32_t count)
+                  uint32_t *d_dirs, size_t dirs_words, void *d_fill, void *d_sort, DevBuf *snapbuf, cudaStream_t st,
+                  uint32_t first, uint32_t count, cudaStream_t stTrace = nullptr, cudaEvent_t evFillDone = nullptr)
 {
+    const bool split = evFillDone != nullptr;      // traceback on its own stream, overlapping the next fill
+    if (!split) stTrace = st;
     BatchClassTable T;
     if (max_n > BATCH_MAX_TEXT || !build_class_table(max_n, std::min(max_m, BATCH_MAX_ROWS), &T)) return SA_ERR_ARGUMENT;
     if (batch_dirs_bound(T, count) > dirs_words) return SA_ERR_MEMORY;
@@ -285,7 +293,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     S.key = S.hist + MAX_CLASSES * SORT_BUCKETS;
     S.order = S.key + count;
     S.dyn = reinterpret_cast<BatchClassDyn *>(reinterpret_cast<char *>(S.order + count) + ((8 - ((uintptr_t)(S.order + count) & 7)) & 7));
-    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx);
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
     SA_TRY(cudaMemsetAsync(S.hist, 0, (size_t)MAX_CLASSES * SORT_BUCKETS * 4, st), SA_ERR_LAUNCH);
     batch_classify_kernel<<<(count + 255) / 256, 256, 0, st>>>(S);
@@ -310,10 +318,24 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
         const uint64_t nTasksMax = ((uint64_t)count + G - 1) / G;
         int grid = (int)std::min<uint64_t>((uint64_t)ctx->sms * occ, (nTasksMax + BATCH_WARPS - 1) / BATCH_WARPS);
         if (grid < 1) grid = 1;
+        if (local) {
+            // arg-max snapshots: one area per resident warp (stays in L2)
+            const size_t need = (size_t)grid * BATCH_WARPS * ((cfg.R + 3) / 4) * 32 * 16;
+            if (need > snapbuf->cap) {
+                SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);          // earlier launches may still use the old buffer
+                SA_TRY(snapbuf->reserve(need), SA_ERR_MEMORY);
+            }
+            A.snap_ws = snapbuf->as<uint4>();
+        }
         SA_TRY(launch_batch_fill(cfg, A, local, grid, smem, st), SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;
     }
     cudaEventRecord(e1, st);
+    if (split) {
+        cudaEventRecord(evFillDone, st);
+        cudaStreamWaitEvent(stTrace, evFillDone, 0);
+    }
+    cudaEventRecord(e2, stTrace);
 
     BatchTraceArgs R{};
     R.text = b->text; R.text_off = b->text_off; R.pattern = b->pattern; R.pattern_off = b->pattern_off;
@@ -322,9 +344,9 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     R.S = ctx->dS.as<int32_t>(); R.alpha = sc->alphabet_size; R.gap = sc->gap; R.local = local;
     std::memcpy(R.alphabet, sc->alphabet, sc->alphabet_size + 1);
     R.results = d_results; R.aln_off = d_alnoff; R.out_text = d_outT; R.out_pattern = d_outP;
-    batch_traceback_kernel<<<(count + 127) / 128, 128, 0, st>>>(R);
+    batch_traceback_kernel<<<(count + 127) / 128, 128, 0, stTrace>>>(R);
     SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
-    cudaEventRecord(e2, st);
+    cudaEventRecord(e3, stTrace);
     ctx->timing.kernel_launches++;
     ctx->timing_dirty = true;
     return SA_OK;
@@ -445,10 +467,11 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
     A.tag_base = (uint32_t)ctx->epoch << 21;
     A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
     SA_TRY(cudaMemsetAsync(A.gmax, 0, 4, st), SA_ERR_LAUNCH);
-    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx);
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
     SA_TRY(launch_long(P.R, A, local, P.grid, P.smem, st), SA_ERR_LAUNCH);
     cudaEventRecord(e1, st);
+    cudaEventRecord(e2, st);
     ctx->timing.kernel_launches++;
 
     const char *tbmode = std::getenv("SA_TB");
@@ -470,7 +493,8 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
         // parallel traceback (sa_traceback.cuh): walkers -> resolve -> count -> offsets -> emit
         TbArgs T{};
         T.Lay.dirs = ctx->dirs.as<uint32_t>(); T.Lay.strip_stride = P.strip_stride;
-        T.Lay.R = P.R; T.Lay.CB = P.CB; T.Lay.NW = P.NW; T.Lay.ROWS = 32 * P.R; T.Lay.n = (int)n; T.Lay.m = (int)m;
+        T.Lay.R = P.R; T.Lay.CB = P.CB; T.Lay.NW = P.NW; T.Lay.ROWS = 32 * P.R;
+        T.Lay.cbShift = P.CB == 1 ? 0 : P.CB == 2 ? 1 : P.CB == 4 ? 2 : 3; T.Lay.n = (int)n; T.Lay.m = (int)m;
         T.text = d_text; T.pattern = d_pat;
         T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
         T.n_strips = P.n_strips;
@@ -515,7 +539,7 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
         }
         SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
     }
-    cudaEventRecord(e2, st);
+    cudaEventRecord(e3, st);
     ctx->timing_dirty = true;
     return SA_OK;
 }
@@ -577,6 +601,8 @@ int sa_create(int device, sa_context **out)
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SA_ERR_NO_DEVICE; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &e : ctx->evFill) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : ctx->evTrace) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &s : ctx->slot) {
         cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
@@ -591,16 +617,20 @@ void sa_destroy(sa_context *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf, &ctx->tbbuf})
+    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf, &ctx->tbbuf, &ctx->snapbuf})
         b->release();
     ctx->pin.release();
     for (auto &s : ctx->slot) {
-        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order}) b->release();
+        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order, &s.snap}) b->release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
     }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->evpool) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->evFill) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->evTrace) if (e) cudaEventDestroy(e);
+    for (auto &b : ctx->pdirs) b.release();
+    for (auto &b : ctx->psort) b.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -612,10 +642,11 @@ int sa_last_timing(const sa_context *cctx, sa_timing *out)
     if (ctx->timing_dirty) {
         // kernel times from the event triples (valid once the caller has synchronised the stream)
         double fill = 0, tb = 0;
-        for (size_t i = 0; i + 2 < ctx->evused + 0 && i + 2 < ctx->evpool.size() + 0; i += 3) {
-            if (cudaEventQuery(ctx->evpool[i + 2]) != cudaSuccess) { cudaGetLastError(); return SA_ERR_LAUNCH; }
+        // (fill start, fill end, traceback start, traceback end) per chunk
+        for (size_t i = 0; i + 3 < ctx->evused && i + 3 < ctx->evpool.size(); i += 4) {
+            if (cudaEventQuery(ctx->evpool[i + 3]) != cudaSuccess) { cudaGetLastError(); return SA_ERR_LAUNCH; }
             fill += ev_us(ctx->evpool[i], ctx->evpool[i + 1]);
-            tb += ev_us(ctx->evpool[i + 1], ctx->evpool[i + 2]);
+            tb += ev_us(ctx->evpool[i + 2], ctx->evpool[i + 3]);
         }
         ctx->timing.fill_us = fill;
         ctx->timing.traceback_us = tb;
@@ -676,7 +707,7 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
         cudaEventRecord(ctx->ev[2], st);
         rc = enqueue_batch(ctx, sc, &b, d_res, d_alnoff, ctx->doutT.as<char>(), ctx->doutP.as<char>(),
                            (uint32_t)n, (uint32_t)m, ctx->dirs.as<uint32_t>(), ctx->dirs.cap / 4, ctx->fill.p,
-                           ctx->sortbuf.p, st, 0, 1);
+                           ctx->sortbuf.p, &ctx->snapbuf, st, 0, 1);
         if (rc) return rc;
         cudaEventRecord(ctx->ev[3], st);
         SA_TRY(cudaMemcpyAsync(&hres, d_res, sizeof hres, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
@@ -779,21 +810,37 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     if (rc) return rc;
     BatchClassTable T;
     if (max_n > BATCH_MAX_TEXT || max_m > BATCH_MAX_ROWS || !build_class_table(max_n, max_m, &T)) return SA_ERR_ARGUMENT;
-    // chunk so that the direction workspace stays within the budget
+    // Chunks are software-pipelined: sort+fill of chunk c+1 runs on the caller's stream while the
+    // (latency-bound) traceback of chunk c runs on the context's stream; two buffer sets.
     const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;      // bytes per pair
     uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / perPair));
+    const char *ps = std::getenv("SA_BATCH_PIPELINE");
+    const bool pipeline = !(ps && ps[0] == '0') && b->n_pairs >= 8192;
+    if (pipeline) chunk = std::min<uint64_t>(chunk, (b->n_pairs + 3) / 4);      // at least 4 chunks to overlap
     chunk = std::min<uint64_t>(chunk, b->n_pairs);
-    SA_TRY(ctx->dirs.reserve(batch_dirs_bound(T, chunk) * 4), SA_ERR_MEMORY);
+    for (int k = 0; k < (pipeline ? 2 : 1); ++k) {
+        SA_TRY(ctx->pdirs[k].reserve(batch_dirs_bound(T, chunk) * 4), SA_ERR_MEMORY);
+        SA_TRY(ctx->psort[k].reserve(batch_sort_bytes(chunk)), SA_ERR_MEMORY);
+    }
     SA_TRY(ctx->fill.reserve(b->n_pairs * 12 + 64), SA_ERR_MEMORY);
-    SA_TRY(ctx->sortbuf.reserve(batch_sort_bytes(chunk)), SA_ERR_MEMORY);
     reset_timing(ctx);
     cudaEventRecord(ctx->ev[2], st);
-    for (uint64_t first = 0; first < b->n_pairs; first += chunk) {
+    int c = 0;
+    for (uint64_t first = 0; first < b->n_pairs; first += chunk, ++c) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, b->n_pairs - first);
+        const int k = pipeline ? (c & 1) : 0;
+        if (pipeline && c >= 2) cudaStreamWaitEvent(st, ctx->evTrace[k], 0);      // buffer set k is free again
         rc = enqueue_batch(ctx, sc, b, out->results, out->aln_off, out->aligned_text, out->aligned_pattern,
-                           max_n, max_m, ctx->dirs.as<uint32_t>(), ctx->dirs.cap / 4, ctx->fill.p, ctx->sortbuf.p, st,
-                           (uint32_t)first, count);
+                           max_n, max_m, ctx->pdirs[k].as<uint32_t>(), ctx->pdirs[k].cap / 4, ctx->fill.p, ctx->psort[k].p,
+                           &ctx->snapbuf, st, (uint32_t)first, count, pipeline ? ctx->stream : nullptr,
+                           pipeline ? ctx->evFill[k] : nullptr);
         if (rc) return rc;
+        if (pipeline) cudaEventRecord(ctx->evTrace[k], ctx->stream);
+    }
+    if (pipeline) {
+        // join: the caller's stream continues only after the last tracebacks
+        cudaStreamWaitEvent(st, ctx->evTrace[0], 0);
+        if (c >= 2) cudaStreamWaitEvent(st, ctx->evTrace[1], 0);
     }
     cudaEventRecord(ctx->ev[3], st);
     return SA_OK;
@@ -869,7 +916,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             // members too long for the batch kernels are skipped by the device-side classifier
             // (and aligned one by one below)
             rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
-                               s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, s.stream, 0, (uint32_t)count);
+                               s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, &s.snap, s.stream, 0, (uint32_t)count);
             if (rc) return rc;
             SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);

@@ -58,6 +58,7 @@ struct BatchArgs {
     int alpha;
     int gap;
     uint32_t max_n;           // max text length of this launch (sizes the text stage)
+    uint4 *snap_ws;           // SW: per-warp arg-max snapshot area in global memory (L2-resident)
 };
 
 
@@ -79,14 +80,15 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill_kernel(const BatchArgs 
     const int alpha = A.alpha;
     const uint32_t textPad = (A.max_n + 15u) & ~15u;
     const uint32_t groupBytes = (alpha * PS + textPad + 15u) & ~15u;
-    constexpr uint32_t snapBytes = LOCAL ? ((R + 3) / 4) * 32 * 16 + 16 * G : 0;   // snapshots + per-group bound
+    constexpr uint32_t snapBytes = LOCAL ? 16 * G : 0;                   // per-group arg-max bound
 
     int8_t *S4s = reinterpret_cast<int8_t *>(smem);                          // alpha x 32
     unsigned char *wbase = smem + 32 * MAX_ALPHA + (size_t)warp * (G * groupBytes + snapBytes);
     unsigned char *profS = wbase + (size_t)g * groupBytes;
     unsigned char *textS = profS + alpha * PS;
-    uint4 *snap = reinterpret_cast<uint4 *>(wbase + G * groupBytes);
-    int *gmS = reinterpret_cast<int *>(wbase + G * groupBytes + ((R + 3) / 4) * 32 * 16) + 4 * g;
+    // the snapshots live in global memory: written on records only, read back by the same lane
+    uint4 *snap = A.snap_ws + (size_t)(blockIdx.x * WARPS + warp) * (((R + 3) / 4) * 32);
+    int *gmS = reinterpret_cast<int *>(wbase + G * groupBytes) + 4 * g;
 
     for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
     __syncthreads();
@@ -304,6 +306,13 @@ struct BatchTraceArgs {
 
 __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceArgs A)
 {
+    // alphabet and score matrix in shared memory: per-lane indices differ, and a divergent index into
+    // the constant bank (kernel parameters) would serialise
+    __shared__ char alphS[MAX_ALPHA + 1];
+    __shared__ int SS[MAX_ALPHA * MAX_ALPHA];
+    for (int i = threadIdx.x; i <= A.alpha; i += blockDim.x) alphS[i] = A.alphabet[i];
+    for (int i = threadIdx.x; i < A.alpha * A.alpha; i += blockDim.x) SS[i] = A.S[i];
+    __syncthreads();
     const uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x;
     if (gpos >= A.dyn[A.table.n_classes].first) return;
     int cls = 0;
@@ -317,23 +326,65 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     const int n = (int)(A.text_off[pair + 1] - t0), m = (int)(A.pattern_off[pair + 1] - p0);
     const uint8_t *tx = A.text + t0, *pt = A.pattern + p0;
     const uint32_t *dbase = A.dirs + A.dyn[cls].dir_base + (size_t)task * A.table.stride[cls] + g * cL;
-    const char GAPC = A.alphabet[A.alpha];
+    const char GAPC = alphS[A.alpha];
     const uint64_t slotEnd = (uint64_t)(t0 + p0) + (uint64_t)(n + m);
-    char *oT = A.out_text + slotEnd, *oP = A.out_pattern + slotEnd;
 
     int i = (int)A.end_i[pair], j = (int)A.end_j[pair];
     int H = A.score[pair];
     uint64_t len = 0;
     size_t cachedAddr = ~(size_t)0; uint32_t cachedWord = 0;
 
-    auto fetch = [&](int ii, int jj) -> int {
-        const int ll = (ii - 1) / cR, r = (ii - 1) % cR;
+    // The walk is bound by L1TEX sector traffic (every lane touches its own pair), so everything is
+    // moved in aligned 32-bit words: residues are read a word at a time and kept in registers, output
+    // characters are packed and stored a word at a time.
+    struct WordReader {
+        const uint32_t *base; int off; int curw; uint32_t w;
+        __device__ WordReader(const uint8_t *p) : base(reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3)),
+                                                   off((int)(reinterpret_cast<uintptr_t>(p) & 3)), curw(-1), w(0) {}
+        __device__ __forceinline__ int get(int q) {
+            const int a = q + off, wi = a >> 2;
+            if (wi != curw) { curw = wi; w = base[wi]; }
+            return (int)((w >> ((a & 3) * 8)) & 0xffu);
+        }
+    };
+    WordReader rdT(tx), rdP(pt);
+
+    // (lane, row-in-lane) of DP row i, kept incrementally: no integer division in the walk
+    int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
+    const int cbShift = cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3;
+    auto fetch = [&](int jj) -> int {
         const int k = (jj - 1) + ll;
-        const int kb = k / cCB, kk = k % cCB;
+        const int kb = k >> cbShift, kk = k & (cCB - 1);
         const int bit = (kk * cR + r) * 2;
         const size_t addr = (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
         if (addr != cachedAddr) { cachedAddr = addr; cachedWord = dbase[addr]; }
         return (cachedWord >> (bit & 31)) & 3;
+    };
+    auto row_up = [&]() { --i; if (r == 0) { r = cR - 1; --ll; } else --r; };
+
+    // backwards writer: bytes go to decreasing addresses; whole aligned words when possible
+    char *const baseT = A.out_text, *const baseP = A.out_pattern;
+    const bool wordOK = ((reinterpret_cast<uintptr_t>(baseT) ^ reinterpret_cast<uintptr_t>(baseP)) & 3) == 0;
+    uint64_t wp = slotEnd;                       // the next byte goes to wp-1
+    uint32_t accT = 0, accP = 0; int cnt = 0;
+    auto emit = [&](const unsigned cT, const unsigned cP) {
+        --wp;
+        const bool top = (reinterpret_cast<uintptr_t>(baseT + wp) & 3) == 3;
+        if (!wordOK || (cnt == 0 && !top)) { baseT[wp] = (char)cT; baseP[wp] = (char)cP; return; }
+        accT = (accT << 8) | cT;                  // little-endian: the lowest address ends up in bits 7:0
+        accP = (accP << 8) | cP;
+        if (++cnt == 4) {
+            *reinterpret_cast<uint32_t *>(baseT + wp) = accT;
+            *reinterpret_cast<uint32_t *>(baseP + wp) = accP;
+            cnt = 0;
+        }
+    };
+    auto flush = [&]() {
+        for (int q = 0; q < cnt; ++q) {
+            baseT[wp + q] = (char)((accT >> (8 * q)) & 0xffu);
+            baseP[wp + q] = (char)((accP >> (8 * q)) & 0xffu);
+        }
+        cnt = 0;
     };
 
     int ti, pi;
@@ -343,30 +394,32 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
             int tag;
             if (j == 0) tag = TAG_TOP;             // alignSequenceCPU.cpp:78-79
             else if (i == 0) tag = TAG_LEFT;       // :80-81
-            else tag = fetch(i, j);
+            else tag = fetch(j);
             const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
             ++len;
-            oT[-(int64_t)len] = takeT ? A.alphabet[tx[ti]] : GAPC;
-            oP[-(int64_t)len] = takeP ? A.alphabet[pt[pi]] : GAPC;
+            emit(takeT ? (unsigned)alphS[rdT.get(ti)] : (unsigned)GAPC, takeP ? (unsigned)alphS[rdP.get(pi)] : (unsigned)GAPC);
             ti = max(0, ti - (int)takeT);
             pi = max(0, pi - (int)takeP);
-            i -= takeP; j -= takeT;
+            if (takeP) row_up();
+            j -= takeT;
         }
     } else {
         ti = j - 1; pi = i - 1;                    // :13-14 (-1/-1 when the best score is 0)
         while (H > 0) {                            // H(i,j) == 0  <=>  reference STOP
-            const int tag = fetch(i, j);
+            const int tag = fetch(j);
             const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
             ++len;
-            oT[-(int64_t)len] = takeT ? A.alphabet[tx[ti]] : GAPC;
-            oP[-(int64_t)len] = takeP ? A.alphabet[pt[pi]] : GAPC;
-            if (tag == TAG_DIAG) H -= A.S[pt[i - 1] * A.alpha + tx[j - 1]]; else H += A.gap;
-            i -= takeP; j -= takeT;
+            const int ct = rdT.get(ti), cp = rdP.get(pi);      // ti == j-1 and pi == i-1 inside the matrix
+            emit(takeT ? (unsigned)alphS[ct] : (unsigned)GAPC, takeP ? (unsigned)alphS[cp] : (unsigned)GAPC);
+            if (tag == TAG_DIAG) H -= SS[cp * A.alpha + ct]; else H += A.gap;
+            if (takeP) row_up();
+            j -= takeT;
             if (i == 0 || j == 0) break;           // :45-46, before the index update
             ti = max(0, ti - (int)takeT);
             pi = max(0, pi - (int)takeP);
         }
     }
+    flush();
     sa_result res;
     res.score = A.score[pair];
     res.aln_len = len;

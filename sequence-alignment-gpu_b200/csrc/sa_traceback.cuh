@@ -27,7 +27,7 @@ namespace sa {
 
 struct TbLayout {
     const uint32_t *dirs;  uint64_t strip_stride;
-    int R, CB, NW, ROWS;
+    int R, CB, NW, ROWS, cbShift;
     int n, m;
 };
 
@@ -75,10 +75,11 @@ struct TbCursor {
 // direction tag of cell (i, j), 1 <= i <= m, 1 <= j <= n
 __device__ __forceinline__ int tb_fetch(const TbLayout &L, TbCursor &cur, const int i, const int j)
 {
-    const int s = (i - 1) / L.ROWS, rr = (i - 1) % L.ROWS;
-    const int ll = rr / L.R, r = rr % L.R;
+    // one division by R; ROWS = 32*R and CB is a power of two
+    const int gl = (i - 1) / L.R, r = (i - 1) - gl * L.R;
+    const int s = gl >> 5, ll = gl & 31;
     const int k = (j - 1) + ll;
-    const int kb = k / L.CB, kk = k % L.CB;
+    const int kb = k >> L.cbShift, kk = k & (L.CB - 1);
     const int bit = (kk * L.R + r) * 2;
     const size_t addr = (size_t)s * L.strip_stride + (size_t)(kb * L.NW + (bit >> 5)) * 32 + ll;
     if (addr != cur.cachedAddr) { cur.cachedAddr = addr; cur.cachedWord = __ldg(L.dirs + addr); }

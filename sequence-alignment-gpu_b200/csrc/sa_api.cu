@@ -4,6 +4,7 @@
 // every compute entry fails with SA_ERR_NO_DEVICE when there is no GPU.
 #include "../../include/sa_b200.h"
 #include "sa_batch.cuh"
+#include "sa_batch16.cuh"
 #include "sa_long.cuh"
 #include "sa_traceback.cuh"
 
@@ -151,7 +152,7 @@ struct BatchCfg { int R, L; };
 const BatchCfg kBatchCfgs[] = {{8, 16}, {12, 16}, {16, 16}, {20, 16}, {24, 16}, {16, 32}, {24, 32}, {32, 32}, {48, 32}};
 // every instantiation of batch_fill_kernel
 #define SA_BATCH_CFG_LIST(X) X(8, 8) X(16, 8) X(32, 8) X(40, 8) X(48, 8) X(8, 16) X(12, 16) X(16, 16) X(20, 16) X(24, 16) \
-    X(8, 32) X(10, 32) X(12, 32) X(16, 32) X(24, 32) X(32, 32) X(48, 32)
+    X(4, 32) X(6, 32) X(8, 32) X(10, 32) X(12, 32) X(16, 32) X(24, 32) X(32, 32) X(48, 32)
 #ifndef SA_BATCH_WARPS
 #define SA_BATCH_WARPS 4
 #endif
@@ -167,23 +168,35 @@ bool cfg_exists(int R, int L)
     return false;
 }
 
-size_t batch_task_stride(const BatchCfg &c, uint32_t max_n)
+size_t batch_task_stride(const BatchCfg &c, uint32_t max_n, bool packed)
 {
-    const int CB = cb_for(c.R), NW = c.R * CB / 16;
+    const int CB = packed ? cb16_for(c.R) : cb_for(c.R), NW = c.R * CB / (packed ? 8 : 16);
     const size_t nblocks = ((size_t)max_n + c.L - 1 + CB - 1) / CB;
     return nblocks * NW * 32;
 }
 
-size_t batch_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n, bool local)
+size_t batch_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n, bool local, bool packed)
 {
     const int G = 32 / c.L;
     const size_t group = ((size_t)alpha * c.L * rpad_for(c.R) + ((max_n + 15u) & ~15u) + 15u) & ~(size_t)15;
     const size_t snap = local ? (size_t)16 * G : 0;
-    return 32 * MAX_ALPHA + (size_t)BATCH_WARPS * (G * group + snap);
+    return 32 * MAX_ALPHA + (size_t)BATCH_WARPS * ((packed ? 2 : 1) * G * group + snap);
+}
+
+// s16x2 kernels exist for the 16-lane classes
+#define SA_BATCH16_CFG_LIST(X) X(8, 16) X(12, 16) X(16, 16) X(20, 16) X(24, 16) X(4, 32) X(6, 32) X(8, 32) X(10, 32) X(12, 32)
+// default classes when the scores fit 16 bits: a whole warp per PAIR OF PAIRS (keeps 12 warps per SM)
+const BatchCfg kBatchCfgs16[] = {{4, 32}, {6, 32}, {8, 32}, {10, 32}, {12, 32}, {16, 32}, {24, 32}, {32, 32}, {48, 32}};
+bool cfg16_exists(int R, int L)
+{
+#define X(r, l) if (R == r && L == l) return true;
+    SA_BATCH16_CFG_LIST(X)
+#undef X
+    return false;
 }
 
 // Classes needed for patterns up to max_m and texts up to max_n.  Returns false if max_m is not covered.
-bool build_class_table(uint32_t max_n, uint32_t max_m, BatchClassTable *T)
+bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, BatchClassTable *T)
 {
     std::vector<BatchCfg> cfgs;
     if (const char *e = std::getenv("SA_BATCH_CLASSES")) {
@@ -196,14 +209,17 @@ bool build_class_table(uint32_t max_n, uint32_t max_m, BatchClassTable *T)
         }
         std::sort(cfgs.begin(), cfgs.end(), [](const BatchCfg &x, const BatchCfg &y) { return x.R * x.L < y.R * y.L; });
     }
-    if (cfgs.empty() || (uint32_t)(cfgs.back().R * cfgs.back().L) < max_m)
-        cfgs.assign(std::begin(kBatchCfgs), std::end(kBatchCfgs));
+    if (cfgs.empty() || (uint32_t)(cfgs.back().R * cfgs.back().L) < max_m) {
+        if (allow16) cfgs.assign(std::begin(kBatchCfgs16), std::end(kBatchCfgs16));
+        else cfgs.assign(std::begin(kBatchCfgs), std::end(kBatchCfgs));
+    }
     std::memset(T, 0, sizeof *T);
     for (const BatchCfg &c : cfgs) {
         if (T->n_classes == MAX_CLASSES) break;
         const int k = T->n_classes++;
         T->R[k] = c.R; T->L[k] = c.L; T->max_rows[k] = (uint32_t)(c.R * c.L);
-        T->stride[k] = batch_task_stride(c, max_n);
+        T->packed[k] = allow16 && cfg16_exists(c.R, c.L);
+        T->stride[k] = batch_task_stride(c, max_n, T->packed[k] != 0);
         if ((uint32_t)(c.R * c.L) >= max_m) break;      // larger classes cannot occur
     }
     T->max_text = BATCH_MAX_TEXT;
@@ -219,7 +235,7 @@ size_t batch_dirs_bound(const BatchClassTable &T, uint64_t count)
     double perPair = 0;
     size_t round = 0;
     for (int c = 0; c < T.n_classes; ++c) {
-        perPair = std::max(perPair, (double)T.stride[c] / (32 / T.L[c]));
+        perPair = std::max(perPair, (double)T.stride[c] / ((32 / T.L[c]) * (T.packed[c] ? 2 : 1)));
         round += T.stride[c];
     }
     return (size_t)(perPair * (double)count) + round + 64;
@@ -250,6 +266,55 @@ int occupancy_batch_t(bool local, size_t smem)
     return nb;
 }
 
+template <int R, int L>
+cudaError_t launch_batch_fill16_t(const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+{
+    if (local) batch_fill16_kernel<R, L, true, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A);
+    else batch_fill16_kernel<R, L, false, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int R, int L>
+int occupancy_batch16_t(bool local, size_t smem)
+{
+    int nb = 0;
+    if (local) {
+        cudaFuncSetAttribute(batch_fill16_kernel<R, L, true, BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, batch_fill16_kernel<R, L, true, BATCH_WARPS>, BATCH_WARPS * 32, smem);
+    } else {
+        cudaFuncSetAttribute(batch_fill16_kernel<R, L, false, BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, batch_fill16_kernel<R, L, false, BATCH_WARPS>, BATCH_WARPS * 32, smem);
+    }
+    return nb;
+}
+cudaError_t launch_batch_fill16(const BatchCfg &cfg, const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+{
+#define X(r, l) if (cfg.R == r && cfg.L == l) return launch_batch_fill16_t<r, l>(A, local, grid, smem, st);
+    SA_BATCH16_CFG_LIST(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+int occupancy_batch16(const BatchCfg &cfg, bool local, size_t smem)
+{
+#define X(r, l) if (cfg.R == r && cfg.L == l) return occupancy_batch16_t<r, l>(local, smem);
+    SA_BATCH16_CFG_LIST(X)
+#undef X
+    return 0;
+}
+
+// 16-bit range guard of the s16x2 kernels: every value the packed arithmetic can produce must fit.
+bool fits_s16(const sa_scoring *sc, uint32_t max_n, uint32_t max_m)
+{
+    if (const char *e = std::getenv("SA_BATCH_S16")) if (e[0] == '0') return false;
+    long long smax = 0, smin = 0;
+    const int a = sc->alphabet_size;
+    for (int i = 0; i < a * a; ++i) { smax = std::max<long long>(smax, sc->score_matrix[i]); smin = std::min<long long>(smin, sc->score_matrix[i]); }
+    const long long g = sc->gap, lo = std::min<long long>(max_n, max_m), sum = (long long)max_n + max_m;
+    const long long up = smax * lo;                                     // best possible score
+    const long long down = sc->mode == SA_LOCAL ? 0 : std::max(g, -smin) * sum;   // worst global score
+    const long long slack = 4 * (std::max(g, std::max(smax, -smin)) + 40);
+    return 4 * std::max(up, down) + slack < 32000;
+}
+
 cudaError_t launch_batch_fill(const BatchCfg &cfg, const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
 {
 #define X(r, l) if (cfg.R == r && cfg.L == l) return launch_batch_fill_t<r, l>(A, local, grid, smem, st);
@@ -278,7 +343,8 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     const bool split = evFillDone != nullptr;      // traceback on its own stream, overlapping the next fill
     if (!split) stTrace = st;
     BatchClassTable T;
-    if (max_n > BATCH_MAX_TEXT || !build_class_table(max_n, std::min(max_m, BATCH_MAX_ROWS), &T)) return SA_ERR_ARGUMENT;
+    if (max_n > BATCH_MAX_TEXT || !build_class_table(max_n, std::min(max_m, BATCH_MAX_ROWS), fits_s16(sc, max_n, max_m), &T))
+        return SA_ERR_ARGUMENT;
     if (batch_dirs_bound(T, count) > dirs_words) return SA_ERR_MEMORY;
     const bool local = sc->mode == SA_LOCAL;
 
@@ -305,29 +371,31 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     // ---- fill: one launch per class; empty classes exit at once ----
     for (int c = 0; c < T.n_classes; ++c) {
         const BatchCfg cfg{T.R[c], T.L[c]};
-        const int G = 32 / cfg.L;
-        const size_t smem = batch_smem_bytes(cfg, sc->alphabet_size, max_n, local);
+        const bool packed = T.packed[c] != 0;
+        const int G = (32 / cfg.L) * (packed ? 2 : 1);                  // pairs per warp task
+        const size_t smem = batch_smem_bytes(cfg, sc->alphabet_size, max_n, local, packed);
         if (smem > (size_t)ctx->smem_optin) return SA_ERR_ARGUMENT;
         BatchArgs A{};
         A.text = b->text; A.text_off = b->text_off; A.pattern = b->pattern; A.pattern_off = b->pattern_off;
         A.order = S.order; A.dyn = S.dyn + c; A.dirs = d_dirs; A.task_stride = T.stride[c];
         A.score = d_score; A.end_i = d_ei; A.end_j = d_ej;
         A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap; A.max_n = max_n;
-        int occ = occupancy_batch(cfg, local, smem);
+        int occ = packed ? occupancy_batch16(cfg, local, smem) : occupancy_batch(cfg, local, smem);
         if (occ < 1) return SA_ERR_LAUNCH;
         const uint64_t nTasksMax = ((uint64_t)count + G - 1) / G;
         int grid = (int)std::min<uint64_t>((uint64_t)ctx->sms * occ, (nTasksMax + BATCH_WARPS - 1) / BATCH_WARPS);
         if (grid < 1) grid = 1;
         if (local) {
             // arg-max snapshots: one area per resident warp (stays in L2)
-            const size_t need = (size_t)grid * BATCH_WARPS * ((cfg.R + 3) / 4) * 32 * 16;
+            const size_t need = (size_t)grid * BATCH_WARPS * ((cfg.R + 3) / 4) * 32 * 16 * (packed ? 2 : 1);
             if (need > snapbuf->cap) {
                 SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);          // earlier launches may still use the old buffer
                 SA_TRY(snapbuf->reserve(need), SA_ERR_MEMORY);
             }
             A.snap_ws = snapbuf->as<uint4>();
         }
-        SA_TRY(launch_batch_fill(cfg, A, local, grid, smem, st), SA_ERR_LAUNCH);
+        SA_TRY(packed ? launch_batch_fill16(cfg, A, local, grid, smem, st) : launch_batch_fill(cfg, A, local, grid, smem, st),
+               SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;
     }
     cudaEventRecord(e1, st);
@@ -699,7 +767,7 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
         SA_TRY(cudaMemcpyAsync(d_offs, hoffs, sizeof hoffs, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
         SA_TRY(cudaStreamSynchronize(st), SA_ERR_COPY);
         BatchClassTable T;
-        if (!build_class_table((uint32_t)n, (uint32_t)m, &T)) return SA_ERR_ARGUMENT;
+        if (!build_class_table((uint32_t)n, (uint32_t)m, fits_s16(sc, (uint32_t)n, (uint32_t)m), &T)) return SA_ERR_ARGUMENT;
         SA_TRY(ctx->dirs.reserve(batch_dirs_bound(T, 1) * 4), SA_ERR_MEMORY);
         SA_TRY(ctx->fill.reserve(64), SA_ERR_MEMORY);
         SA_TRY(ctx->sortbuf.reserve(batch_sort_bytes(1)), SA_ERR_MEMORY);
@@ -809,7 +877,8 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     int rc = upload_scoring(ctx, sc, st);
     if (rc) return rc;
     BatchClassTable T;
-    if (max_n > BATCH_MAX_TEXT || max_m > BATCH_MAX_ROWS || !build_class_table(max_n, max_m, &T)) return SA_ERR_ARGUMENT;
+    if (max_n > BATCH_MAX_TEXT || max_m > BATCH_MAX_ROWS || !build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), &T))
+        return SA_ERR_ARGUMENT;
     // Chunks are software-pipelined: sort+fill of chunk c+1 runs on the caller's stream while the
     // (latency-bound) traceback of chunk c runs on the context's stream; two buffer sets.
     const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;      // bytes per pair
@@ -877,7 +946,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
 
     if (max_m > 0) {
         BatchClassTable T;
-        if (!build_class_table(max_n, max_m, &T)) return SA_ERR_ARGUMENT;
+        if (!build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), &T)) return SA_ERR_ARGUMENT;
         // chunk size: bounded by the direction budget and by ~1/8 of the batch for copy/compute overlap
         const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;
         uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / NSLOT / perPair));

@@ -32,6 +32,7 @@ constexpr int SORT_BUCKETS = 512;
 struct BatchClassTable {            // static description, passed by value
     int n_classes;
     int R[MAX_CLASSES], L[MAX_CLASSES];
+    int packed[MAX_CLASSES];        // 1: s16x2 kernel, two pairs per lane group (sa_batch16.cuh)
     uint32_t max_rows[MAX_CLASSES];
     unsigned long long stride[MAX_CLASSES];     // direction words per task
     uint32_t max_text;              // pairs with a longer text are skipped (host aligns them one by one)
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(1024) batch_scan_kernel(const BatchSortArgs A)
             A.dyn[c].first = first;
             A.dyn[c].count = end - first;
             A.dyn[c].dir_base = dirBase;
-            const uint32_t G = 32 / A.table.L[c];
+            const uint32_t G = (32 / A.table.L[c]) * (A.table.packed[c] ? 2 : 1);      // pairs per task
             dirBase += (unsigned long long)((end - first + G - 1) / G) * A.table.stride[c];
         }
         A.dyn[A.table.n_classes].first = part[1023];
@@ -317,11 +318,17 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     if (gpos >= A.dyn[A.table.n_classes].first) return;
     int cls = 0;
     while (gpos >= A.dyn[cls].first + A.dyn[cls].count) ++cls;
-    const int cR = A.table.R[cls], cL = A.table.L[cls], cCB = cb_for(cR);
-    const int G = 32 / cL, NW = cR * cCB / 16;
+    const int cR = A.table.R[cls], cL = A.table.L[cls];
+    const bool packed = A.table.packed[cls] != 0;
+    // s32 layout: 16 cells per word; s16x2 layout: 8 cells per half-word, the pair's half picked by parity
+    const int cCB = packed ? ((cR % 8 == 0) ? 1 : (cR % 4 == 0) ? 2 : 4) : cb_for(cR);
+    const int cellShift = packed ? 3 : 4;
+    const int G = 32 / cL, NW = (cR * cCB) >> cellShift;
     const uint32_t pos = gpos - A.dyn[cls].first;
     const uint32_t pair = A.order[gpos];
-    const uint32_t task = pos / G, g = pos % G;
+    const uint32_t unit = packed ? pos >> 1 : pos;
+    const int halfBit = packed ? (int)(pos & 1) * 16 : 0;
+    const uint32_t task = unit / G, g = unit % G;
     const int64_t t0 = A.text_off[pair], p0 = A.pattern_off[pair];
     const int n = (int)(A.text_off[pair + 1] - t0), m = (int)(A.pattern_off[pair + 1] - p0);
     const uint8_t *tx = A.text + t0, *pt = A.pattern + p0;
@@ -355,10 +362,10 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     auto fetch = [&](int jj) -> int {
         const int k = (jj - 1) + ll;
         const int kb = k >> cbShift, kk = k & (cCB - 1);
-        const int bit = (kk * cR + r) * 2;
-        const size_t addr = (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        const int cell = kk * cR + r;
+        const size_t addr = (size_t)(kb * NW + (cell >> cellShift)) * 32 + ll;
         if (addr != cachedAddr) { cachedAddr = addr; cachedWord = dbase[addr]; }
-        return (cachedWord >> (bit & 31)) & 3;
+        return (cachedWord >> (2 * (cell & ((1 << cellShift) - 1)) + halfBit)) & 3;
     };
     auto row_up = [&]() { --i; if (r == 0) { r = cR - 1; --ll; } else --r; };
 

@@ -48,15 +48,17 @@ __host__ __device__ constexpr int onehot(int r) { return 1 << (8 * (r & 3)); }
 
 // Profile slice of one lane: R bytes (4*S[p_row][letter] for the lane's R rows), padded to
 // RPAD bytes so that the widest aligned shared-memory load can be used.
-__host__ __device__ constexpr int rpad_for(int R) { return R <= 4 ? 4 : (R + 7) / 8 * 8; }
+__host__ __device__ constexpr int rpad_for(int R) { return (R + 3) / 4 * 4; }
 
 template <int R>
 __device__ __forceinline__ void load_profile_words(const unsigned char *p, uint32_t (&prof)[(R + 3) / 4])
 {
     constexpr int RPAD = rpad_for(R);
     constexpr int NPW = (R + 3) / 4;
-    if constexpr (RPAD == 4) {
-        prof[0] = *reinterpret_cast<const uint32_t *>(p);
+    if constexpr (RPAD % 8 != 0) {
+#pragma unroll
+        for (int q = 0; q < RPAD / 4; ++q)
+            if (q < NPW) prof[q < NPW ? q : 0] = reinterpret_cast<const uint32_t *>(p)[q];
     } else if constexpr (RPAD % 16 == 0) {
 #pragma unroll
         for (int q = 0; q < RPAD / 16; ++q) {

@@ -326,8 +326,16 @@ def run_ours(args, rank, world, local_rank):
     ev1.record()
     barrier()
     clocks = sampler.stop()
-    t = al.timing()                     # kernel event triples of the LAST step
-    fill_us, tb_us, launches = t["fill_us"], t["traceback_us"], t["kernel_launches"]
+    t = al.timing()                     # kernel events of the LAST step
+    launches = t["kernel_launches"]
+    # kernel durations for the roofline: one extra step with the fill/traceback overlap switched off,
+    # so that the CUDA events bracket the fill kernels alone (same kernels, same inputs)
+    os.environ["SA_BATCH_PIPELINE"] = "0"
+    dev_step()
+    barrier()
+    t = al.timing()
+    os.environ.pop("SA_BATCH_PIPELINE", None)
+    fill_us, tb_us = t["fill_us"], t["traceback_us"]
     if w["kind"] == "single":
         step_ms = [x.elapsed_time(y) for x, y in per_step]
         # the L2 flush is not part of the path: use the kernel events of the path itself

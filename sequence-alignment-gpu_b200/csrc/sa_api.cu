@@ -78,6 +78,12 @@ struct sa_context {
     // device-batch pipeline: fills on the caller's stream, tracebacks on `stream`, two buffer sets
     DevBuf pdirs[2], psort[2];
     cudaEvent_t evFill[2] = {}, evTrace[2] = {};
+    // the class kernels of one chunk are independent: they run on side streams so that the tail of
+    // one class overlaps the body of the next
+    static constexpr int NCLS_STREAMS = 4;
+    cudaStream_t clsStream[NCLS_STREAMS] = {};
+    cudaEvent_t evFork = nullptr, evJoin[NCLS_STREAMS] = {};
+    DevBuf clsSnap[NCLS_STREAMS];
     PinBuf pin;
     Slot slot[NSLOT];
     uint32_t epoch = 0;
@@ -368,8 +374,19 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
     ctx->timing.kernel_launches += 3;
 
-    // ---- fill: one launch per class; empty classes exit at once ----
+    // ---- fill: one launch per class; empty classes exit at once.  With SA_BATCH_CLASS_STREAMS (default
+    // on for big chunks) the classes run concurrently on side streams (fork/join by events) ----
+    const char *cse = std::getenv("SA_BATCH_CLASS_STREAMS");
+    const bool forkClasses = snapbuf == &ctx->snapbuf && count >= 4096 && T.n_classes > 1 && !(cse && cse[0] == '0');
+    if (forkClasses) cudaEventRecord(ctx->evFork, st);
+    const cudaStream_t stMain = st;
     for (int c = 0; c < T.n_classes; ++c) {
+        const int lane_ = c % sa_context::NCLS_STREAMS;
+        if (forkClasses) {
+            st = ctx->clsStream[lane_];
+            if (c < sa_context::NCLS_STREAMS) cudaStreamWaitEvent(st, ctx->evFork, 0);
+            snapbuf = &ctx->clsSnap[lane_];
+        }
         const BatchCfg cfg{T.R[c], T.L[c]};
         const bool packed = T.packed[c] != 0;
         const int G = (32 / cfg.L) * (packed ? 2 : 1);                  // pairs per warp task
@@ -397,6 +414,13 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
         SA_TRY(packed ? launch_batch_fill16(cfg, A, local, grid, smem, st) : launch_batch_fill(cfg, A, local, grid, smem, st),
                SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;
+    }
+    st = stMain;
+    if (forkClasses) {
+        for (int k = 0; k < std::min(T.n_classes, (int)sa_context::NCLS_STREAMS); ++k) {
+            cudaEventRecord(ctx->evJoin[k], ctx->clsStream[k]);
+            cudaStreamWaitEvent(st, ctx->evJoin[k], 0);
+        }
     }
     cudaEventRecord(e1, st);
     if (split) {
@@ -670,6 +694,9 @@ int sa_create(int device, sa_context **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SA_ERR_NO_DEVICE; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->evFill) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &st : ctx->clsStream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
+    for (auto &e : ctx->evJoin) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : ctx->evTrace) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &s : ctx->slot) {
         cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -697,6 +724,10 @@ void sa_destroy(sa_context *ctx)
     for (auto &e : ctx->evpool) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->evFill) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->evTrace) if (e) cudaEventDestroy(e);
+    for (auto &st : ctx->clsStream) if (st) cudaStreamDestroy(st);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    for (auto &e : ctx->evJoin) if (e) cudaEventDestroy(e);
+    for (auto &b : ctx->clsSnap) b.release();
     for (auto &b : ctx->pdirs) b.release();
     for (auto &b : ctx->psort) b.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -142,6 +142,13 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill_kernel(const BatchArgs 
         const int nSteps = nmax + L - 1;
         uint32_t *dbase = dirs + (size_t)task * A.task_stride + lane;
 
+        // the profile words of a step are fetched one step ahead (text -> profile is two dependent
+        // shared-memory loads that would otherwise sit in front of every column sweep)
+        uint32_t profN[NPW];
+#pragma unroll
+        for (int q = 0; q < NPW; ++q) profN[q] = 0;
+        if (valid && l == 0 && n > 0) load_profile_words<R>(profS + min((int)textS[0], alpha - 1) * PS, profN);
+
         for (int kb = 0; kb * CB < nSteps; ++kb) {
             uint32_t acc[NW];
 #pragma unroll
@@ -150,18 +157,21 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill_kernel(const BatchArgs 
             for (int kk = 0; kk < CB; ++kk) {
                 const int jt = kb * CB + kk - l;                 // text index of this lane at this step
                 const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
+                uint32_t prof[NPW];
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) prof[q] = profN[q];
+                if (valid && jt + 1 >= 0 && jt + 1 < n)
+                    load_profile_words<R>(profS + min((int)textS[jt + 1], alpha - 1) * PS + l * RPAD, profN);
+                int floorv = 0;
+                if (LOCAL) floorv = *reinterpret_cast<volatile int *>(gmS);
                 if (valid && jt >= 0 && jt < n) {
                     const int top = (l == 0) ? (LOCAL ? 0 : -SCALE * A.gap * (jt + 1)) : up;
-                    const int a = min((int)textS[jt], alpha - 1);
-                    uint32_t prof[NPW];
-                    load_profile_words<R>(profS + a * PS + l * RPAD, prof);
                     int bmax[nblk_for(R)];
                     sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
                     prevTop = top;
                     bottom = c[R - 1];
                     if (LOCAL) {
                         const int colmax = max_of_blocks(bmax);
-                        const int floorv = *reinterpret_cast<volatile int *>(gmS);
                         if (l * R < m && track_argmax<R>(c, colmax, jt + 1, snap, lane, floorv, bestv, bestj))
                             atomicMax(gmS, colmax);
                     }

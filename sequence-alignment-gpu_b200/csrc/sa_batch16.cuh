@@ -209,6 +209,16 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill16_kernel(const BatchArg
         const int rmA = mA > 0 ? (mA - 1) % R : 0, lmA = mA > 0 ? (mA - 1) / R : -1;
         const int rmB = mB > 0 ? (mB - 1) % R : 0, lmB = mB > 0 ? (mB - 1) / R : -1;
 
+        // the profile words of a step are fetched one step ahead (text -> profile is two dependent
+        // shared-memory loads that would otherwise sit in front of every column sweep)
+        uint32_t paN[NPW], pbN[NPW];
+#pragma unroll
+        for (int q = 0; q < NPW; ++q) { paN[q] = 0; pbN[q] = 0; }
+        if (validA && l == 0 && nG > 0) {
+            load_profile_words<R>(profA + (int)textA[0] * PS, paN);
+            load_profile_words<R>(profB + (int)textB[0] * PS, pbN);
+        }
+
         for (int kb = 0; kb * CB < nSteps; ++kb) {
             uint32_t acc[NW];
 #pragma unroll
@@ -217,12 +227,18 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill16_kernel(const BatchArg
             for (int kk = 0; kk < CB; ++kk) {
                 const int jt = kb * CB + kk - l;
                 const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
+                uint32_t pa[NPW], pb[NPW];
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) { pa[q] = paN[q]; pb[q] = pbN[q]; }
+                if (validA && jt + 1 >= 0 && jt + 1 < nG) {
+                    const int la = textA[jt + 1], lb = textB[jt + 1];
+                    load_profile_words<R>(profA + la * PS + l * RPAD, paN);
+                    load_profile_words<R>(profB + lb * PS + l * RPAD, pbN);
+                }
+                int flA = 0, flB = 0;
+                if (LOCAL) { flA = *reinterpret_cast<volatile int *>(gmS); flB = *reinterpret_cast<volatile int *>(gmS + 1); }
                 if (validA && jt >= 0 && jt < nG) {
                     const uint32_t top = (l == 0) ? (LOCAL ? 0u : (uint32_t)((-SCALE * A.gap * (jt + 1)) & 0xffff) * 0x10001u) : up;
-                    const int la = textA[jt], lb = textB[jt];
-                    uint32_t pa[NPW], pb[NPW];
-                    load_profile_words<R>(profA + la * PS + l * RPAD, pa);
-                    load_profile_words<R>(profB + lb * PS + l * RPAD, pb);
                     uint32_t bmax[nblk_for(R)];
                     sweep_column16<R, LOCAL, NW>(c, top, prevTop, pa, pb, KL2, KT2, acc, R * kk, bmax);
                     prevTop = top;
@@ -232,7 +248,6 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill16_kernel(const BatchArg
 #pragma unroll
                         for (int b = 1; b < nblk_for(R); ++b) cm = __vmaxs2(cm, bmax[b]);
                         const int cmA = half_of<0>(cm), cmB = half_of<1>(cm);
-                        const int flA = *reinterpret_cast<volatile int *>(gmS), flB = *reinterpret_cast<volatile int *>(gmS + 1);
                         if (jt < nA && l * R < mA && track_argmax16<R, 0>(c, cmA, jt + 1, snapA, lane, flA, bestvA, bestjA))
                             atomicMax(gmS, cmA);
                         if (jt < nB && l * R < mB && track_argmax16<R, 1>(c, cmB, jt + 1, snapB, lane, flB, bestvB, bestjB))

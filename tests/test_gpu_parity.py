@@ -225,3 +225,53 @@ def test_long_traceback_variants(aligner, oracle, force_path, monkeypatch, varia
             for gap in (2, 7):
                 assert_same(aligner.align(mode, alpha, mat, gap, t, p), oracle.align(mode, alpha, mat, gap, t, p),
                             (variant, alpha, mode, gap, len(t), len(p)))
+
+
+def test_full_size_c3_known_answer_and_rescore(aligner, oracle):
+    """BASELINE config 3 at full size (100 000 x 95 217 synthetic DNA, NW): the reference CPU's answer for
+    this seeded pair (score 399463, 100254 columns, starts 0/0) plus size-independent
+    properties: re-scoring the emitted alignment reproduces the score, the strings spell the inputs."""
+    import synth
+    t, p = synth.synthetic_pair(100000, 12345, 54321)
+    assert (len(t), len(p)) == (100000, 95217)
+    blast = helpers.matrices()["dna/blast.txt"]
+    a = aligner.align(0, 4, blast, 5, t, p)
+    assert (a.score, a.aln_len, a.start_text, a.start_pattern) == (399463, 100254, 0, 0)
+    assert oracle.rescore(a.aligned_text, a.aligned_pattern, 4, blast, 5) == a.score
+    letters = np.frombuffer(b"ATCG", np.uint8)
+    assert a.aligned_text.replace(b"-", b"") == letters[t].tobytes()
+    assert a.aligned_pattern.replace(b"-", b"") == letters[p].tobytes()
+    # the same pair as a local alignment: properties only (the CPU reference needs 9.5 GB and ~100 s)
+    b = aligner.align(1, 4, blast, 5, t, p)
+    assert b.score >= a.score and oracle.rescore(b.aligned_text, b.aligned_pattern, 4, blast, 5) == b.score
+    s0, s1 = b.start_text, b.start_pattern
+    assert b.aligned_text.replace(b"-", b"") in letters[t].tobytes() and b.aligned_pattern.replace(b"-", b"") in letters[p].tobytes()
+    assert s0 < len(t) and s1 < len(p)
+
+
+def test_full_size_c4_batch_properties(sa, aligner, oracle):
+    """BASELINE config 4 shape (100 000 pairs of the 1 M recipe): every pair's alignment re-scores to its
+    score, a sample is compared field by field with the oracle, s16x2 and s32 kernels agree on all pairs."""
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(100000, seed=2024)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    out = aligner.align_batch(1, 23, mat, 5, T, toff, P, poff)
+    res = out["results"]
+    assert int(res["score"].min()) > 0
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, 100000, 400):
+        got = sa.unpack_batch(out, int(i))
+        assert_same(got, oracle.align(1, 23, mat, 5, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]), int(i))
+    for i in range(0, 100000, 37):
+        got = sa.unpack_batch(out, i)
+        assert oracle.rescore(got.aligned_text, got.aligned_pattern, 23, mat, 5) == got.score, i
+    os.environ["SA_BATCH_S16"] = "0"
+    try:
+        out32 = aligner.align_batch(1, 23, mat, 5, T, toff, P, poff)
+    finally:
+        os.environ.pop("SA_BATCH_S16", None)
+    assert np.array_equal(out32["results"], res)
+    h = lambda o: (o["aligned_text"].tobytes(), o["aligned_pattern"].tobytes(), o["aln_off"].tobytes())
+    k = 5000   # strings of the first pairs byte for byte (the arenas' unused slack is not compared)
+    for i in range(k):
+        assert sa.unpack_batch(out, i).key() == sa.unpack_batch(out32, i).key()

@@ -496,10 +496,11 @@ struct LongPlan {
 int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P)
 {
     const bool local = sc->mode == SA_LOCAL;
-    const uint64_t targetWarps = (uint64_t)ctx->sms * 4;      // one warp per SM sub-partition
-    int R = kLongR[sizeof(kLongR) / sizeof(int) - 1];
-    for (int r : kLongR)
-        if ((m + 32ull * r - 1) / (32ull * r) <= targetWarps) { R = r; break; }
+    // Strip height: measured on B200 (tools/probe_r.py): R = 6 is fastest from 4 k to 100 k rows (the
+    // chain lag per strip, ~150 column-steps, outweighs the cheaper steps of smaller R); beyond that
+    // taller strips keep the number of resident warps near two per SM sub-partition.
+    (void)ctx;
+    int R = m <= 150000 ? 6 : m <= 300000 ? 8 : m <= 450000 ? 12 : 16;
     if (const char *e = std::getenv("SA_LONG_R")) {
         const int r = std::atoi(e);
         for (int k : kLongR) if (k == r) R = r;

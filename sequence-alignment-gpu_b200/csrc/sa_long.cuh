@@ -174,9 +174,12 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
 #pragma unroll
         for (int w = 0; w < NW; ++w) acc[w] = 0;
 
-        // One wavefront step.  FAST = steady state (every lane has a column, upkeep done by the caller).
-        auto step = [&](const int k, const int kk, auto fastTag) {
-            constexpr bool FAST = decltype(fastTag)::value;
+        // One wavefront step.  MODE 1 = steady state (every lane has a column, upkeep done by the
+        // caller), MODE 2 = ramp-up (same, but lanes whose first column has not arrived yet idle),
+        // MODE 0 = generic (all bounds checked; short texts and the drain).
+        auto step = [&](const int k, const int kk, auto modeTag) {
+            constexpr int MODE = decltype(modeTag)::value;
+            constexpr bool FAST = MODE != 0;
             const int jt = k - lane, k1 = k + 1, jn = k1 - lane;
             uint32_t prof[NPW];
 #pragma unroll
@@ -184,11 +187,11 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             const int topv = topN;
             if (!FAST) upkeep(k1);
             // next step's letter first: its shared-memory latency hides behind the sweep below
-            const bool nextActive = FAST || (jn >= 0 && jn < n);
+            const bool nextActive = MODE == 1 || (MODE == 2 ? jn >= 0 : (jn >= 0 && jn < n));
             const int letterN = nextActive ? (int)textWin[jn & 63] : 0;
             topN = topWin[k1 & (2 * PB - 1)];
             const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
-            if (FAST || (jt >= 0 && jt < n)) {
+            if (MODE == 1 || (MODE == 2 ? jt >= 0 : (jt >= 0 && jt < n))) {
                 const int top = (lane == 0) ? topv : up;
                 int bmax[nblk_for(R)];
                 sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
@@ -213,24 +216,29 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             }
         };
 
-        // ramp-up (k < 32), steady state in sub-blocks of 8 steps, drain
-        const int kFast0 = 32, kFast1 = (n >= 64) ? (n / 32) * 32 : 32;
+        // ramp-up (first 32 steps) and steady state in sub-blocks of 8 steps, then the generic drain.
+        // The ramp is on the critical path of the whole strip chain (strip s+1 starts when strip s has
+        // produced its first columns), so it runs the lean path too.
+        const int kFast1 = (n >= 64) ? (n / 32) * 32 : 0;
         const int nStepsPad = (nSteps + CB - 1) / CB * CB;
         int k = 0;
-        for (; k < min(kFast0, nStepsPad); k += CB) {
+        for (; k < min(32, kFast1); k += 8) {
 #pragma unroll
-            for (int kk = 0; kk < CB; ++kk) step(k + kk, kk, std::false_type{});
+            for (int k8 = 0; k8 < 8; ++k8) {
+                if (k8 == 7) upkeep(k + 8);
+                step(k + k8, k8 % CB, std::integral_constant<int, 2>{});
+            }
         }
         for (; k < kFast1; k += 8) {
 #pragma unroll
             for (int k8 = 0; k8 < 8; ++k8) {
                 if (k8 == 7) upkeep(k + 8);
-                step(k + k8, k8 % CB, std::true_type{});
+                step(k + k8, k8 % CB, std::integral_constant<int, 1>{});
             }
         }
         for (; k < nStepsPad; k += CB) {
 #pragma unroll
-            for (int kk = 0; kk < CB; ++kk) step(k + kk, kk, std::false_type{});
+            for (int kk = 0; kk < CB; ++kk) step(k + kk, kk, std::integral_constant<int, 0>{});
         }
 
         // ---- strip results ----

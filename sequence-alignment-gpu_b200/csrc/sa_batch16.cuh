@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill16_kernel(const BatchArg
             load_profile_words<R>(profB + (int)textB[0] * PS, pbN);
         }
 
+        uint32_t upN = 0;
         for (int kb = 0; kb * CB < nSteps; ++kb) {
             uint32_t acc[NW];
 #pragma unroll
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill16_kernel(const BatchArg
 #pragma unroll
             for (int kk = 0; kk < CB; ++kk) {
                 const int jt = kb * CB + kk - l;
-                const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
+                const uint32_t up = upN;                     // exchanged at the end of the previous step
                 uint32_t pa[NPW], pb[NPW];
 #pragma unroll
                 for (int q = 0; q < NPW; ++q) { pa[q] = paN[q]; pb[q] = pbN[q]; }
@@ -237,12 +238,18 @@ __global__ void __launch_bounds__(WARPS * 32) batch_fill16_kernel(const BatchArg
                 }
                 int flA = 0, flB = 0;
                 if (LOCAL) { flA = *reinterpret_cast<volatile int *>(gmS); flB = *reinterpret_cast<volatile int *>(gmS + 1); }
-                if (validA && jt >= 0 && jt < nG) {
+                const bool active = validA && jt >= 0 && jt < nG;
+                uint32_t bmax[nblk_for(R)];
+                if (active) {
                     const uint32_t top = (l == 0) ? (LOCAL ? 0u : (uint32_t)((-SCALE * A.gap * (jt + 1)) & 0xffff) * 0x10001u) : up;
-                    uint32_t bmax[nblk_for(R)];
                     sweep_column16<R, LOCAL, NW>(c, top, prevTop, pa, pb, KL2, KT2, acc, R * kk, bmax);
                     prevTop = top;
                     bottom = c[R - 1];
+                }
+                // the neighbour exchange for the NEXT step is issued before the bookkeeping below, so that
+                // the shuffle latency overlaps it (every lane of the warp executes it)
+                upN = __shfl_up_sync(0xffffffffu, bottom, 1);
+                if (active) {
                     if (LOCAL) {
                         uint32_t cm = bmax[0];
 #pragma unroll

@@ -5,6 +5,7 @@
 #include "../../include/sa_b200.h"
 #include "sa_batch.cuh"
 #include "sa_batch16.cuh"
+#include "sa_batch16_sw.cuh"
 #include "sa_long.cuh"
 #include "sa_traceback.cuh"
 
@@ -307,6 +308,35 @@ int occupancy_batch16(const BatchCfg &cfg, bool local, size_t smem)
     return 0;
 }
 
+// straight-line packed SW kernel (sa_batch16_sw.cuh): L = 32 classes only
+#define SA_SW16_R_LIST(X) X(4) X(6) X(8) X(10) X(12)
+bool sw16_exists(const BatchCfg &cfg)
+{
+    static const bool off = [] { const char *e = std::getenv("SA_BATCH_SW16"); return e && e[0] == '0'; }();
+    if (off || cfg.L != 32) return false;
+#define X(r) if (cfg.R == r) return true;
+    SA_SW16_R_LIST(X)
+#undef X
+    return false;
+}
+size_t sw16_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n) { return 32 * MAX_ALPHA + (size_t)BATCH_WARPS * sw16_warp_bytes(c.R, alpha, max_n); }
+cudaError_t launch_sw16(const BatchCfg &cfg, const BatchArgs &A, int grid, size_t smem, cudaStream_t st)
+{
+#define X(r) if (cfg.R == r) { batch_sw16_kernel<r, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A); return cudaGetLastError(); }
+    SA_SW16_R_LIST(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+int occupancy_sw16(const BatchCfg &cfg, size_t smem)
+{
+    int nb = 0;
+#define X(r) if (cfg.R == r) { cudaFuncSetAttribute(batch_sw16_kernel<r, BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, batch_sw16_kernel<r, BATCH_WARPS>, BATCH_WARPS * 32, smem); }
+    SA_SW16_R_LIST(X)
+#undef X
+    return nb;
+}
+
 // 16-bit range guard of the s16x2 kernels: every value the packed arithmetic can produce must fit.
 bool fits_s16(const sa_scoring *sc, uint32_t max_n, uint32_t max_m)
 {
@@ -390,19 +420,20 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
         const BatchCfg cfg{T.R[c], T.L[c]};
         const bool packed = T.packed[c] != 0;
         const int G = (32 / cfg.L) * (packed ? 2 : 1);                  // pairs per warp task
-        const size_t smem = batch_smem_bytes(cfg, sc->alphabet_size, max_n, local, packed);
+        const bool sw16 = packed && local && sw16_exists(cfg);
+        const size_t smem = sw16 ? sw16_smem_bytes(cfg, sc->alphabet_size, max_n) : batch_smem_bytes(cfg, sc->alphabet_size, max_n, local, packed);
         if (smem > (size_t)ctx->smem_optin) return SA_ERR_ARGUMENT;
         BatchArgs A{};
         A.text = b->text; A.text_off = b->text_off; A.pattern = b->pattern; A.pattern_off = b->pattern_off;
         A.order = S.order; A.dyn = S.dyn + c; A.dirs = d_dirs; A.task_stride = T.stride[c];
         A.score = d_score; A.end_i = d_ei; A.end_j = d_ej;
         A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap; A.max_n = max_n;
-        int occ = packed ? occupancy_batch16(cfg, local, smem) : occupancy_batch(cfg, local, smem);
+        int occ = sw16 ? occupancy_sw16(cfg, smem) : packed ? occupancy_batch16(cfg, local, smem) : occupancy_batch(cfg, local, smem);
         if (occ < 1) return SA_ERR_LAUNCH;
         const uint64_t nTasksMax = ((uint64_t)count + G - 1) / G;
         int grid = (int)std::min<uint64_t>((uint64_t)ctx->sms * occ, (nTasksMax + BATCH_WARPS - 1) / BATCH_WARPS);
         if (grid < 1) grid = 1;
-        if (local) {
+        if (local && !sw16) {
             // arg-max snapshots: one area per resident warp (stays in L2)
             const size_t need = (size_t)grid * BATCH_WARPS * ((cfg.R + 3) / 4) * 32 * 16 * (packed ? 2 : 1);
             if (need > snapbuf->cap) {
@@ -411,7 +442,8 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
             }
             A.snap_ws = snapbuf->as<uint4>();
         }
-        SA_TRY(packed ? launch_batch_fill16(cfg, A, local, grid, smem, st) : launch_batch_fill(cfg, A, local, grid, smem, st),
+        SA_TRY(sw16 ? launch_sw16(cfg, A, grid, smem, st)
+                    : packed ? launch_batch_fill16(cfg, A, local, grid, smem, st) : launch_batch_fill(cfg, A, local, grid, smem, st),
                SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;
     }

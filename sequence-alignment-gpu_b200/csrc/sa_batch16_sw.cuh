@@ -1,0 +1,312 @@
+// sa_batch16_sw.cuh -- packed (s16x2) Smith-Waterman batch fill, straight-line version.
+//
+// Same cell arithmetic, lane mapping and direction layout as batch_fill16_kernel<R, 32, true>
+// (sa_batch16.cuh), but the column loop has no per-step control flow:
+//
+//   * columns outside a pair's text (before a lane's first column, after the last one) read a
+//     SENTINEL letter whose profile row is all 0x80 (= -128).  For SW that keeps not-yet-started
+//     lanes at H = 0 and makes the columns past the end decay (every value there is < the value
+//     it was derived from), so neither needs a predicate, and nothing they write is ever read by
+//     the traceback.
+//   * the text is fetched as one aligned word per FOUR steps (funnel-shifted by the lane's byte
+//     phase) instead of a byte per step.
+//   * the arg-max (reference: first maximum in row-major order, alignSequenceCPU.cpp:150-168) is
+//     tracked per QUAD of four columns: each step only reduces the column to its maximum
+//     (VIMNMX3 tree); once per quad the lane compares the quad maximum with its best and, on a
+//     strict improvement, keeps the quad's START state (R cells + the 4 tops + the diagonal) with
+//     one PRMT per register -- branch-free, the two pairs of the word select independently.
+//     After the sweep the winning quad is replayed (4 columns, once per task) to locate the exact
+//     first cell.  Equal maxima in different quads take a slow path that replays both; it is only
+//     entered while the value is the pair-wide maximum so far (one REDUX.MAX per half and quad).
+//
+// Results are bit-identical to the s32 kernel; tests/test_gpu_parity.py compares all three.
+#pragma once
+#include "sa_batch16.cuh"
+
+namespace sa {
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32_off(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF));
+    return v;
+}
+
+template <int R>
+struct Quad16 {
+    uint32_t c[R];       // the lane's R cells in the column before the quad (packed A|B)
+    uint32_t top[4];     // the value above the lane's first row in the quad's four columns
+    uint32_t diag;       // ... and in the column before
+};
+
+// plain packed SW column (no direction deposit); used by the replay only
+template <int R>
+__device__ __forceinline__ void sw16_column_plain(uint32_t (&c)[R], uint32_t top, uint32_t diag, const uint32_t (&pa)[(R + 3) / 4],
+                                                  const uint32_t (&pb)[(R + 3) / 4], const uint32_t KL2, const uint32_t KT2)
+{
+    uint32_t t = top, d = diag;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t s2 = prmt_sx(pa[r >> 2], pb[r >> 2], sel16(r & 3));
+        const uint32_t m = __viaddmax_s16x2(d, s2, __vadd2(c[r], KL2));
+        const uint32_t cn = __viaddmax_s16x2_relu(t, KT2, m) & 0xFFFCFFFCu;
+        d = c[r];
+        t = cn;
+        c[r] = cn;
+    }
+}
+
+// Re-run the four columns of a quad and return, per half, the key 4*row + column of the row-major
+// first cell equal to that half of v2 (0xFFFF when there is none).
+//   lettersA4/B4: the four letters of the quad (byte k = column k), sprofA/B: the lane's profile base.
+template <int R>
+__device__ __noinline__ uint32_t replay_quad16(const Quad16<R> s, const uint32_t v2, const uint32_t lettersA4, const uint32_t lettersB4,
+                                               const uint32_t sprofA, const uint32_t sprofB, const uint32_t KL2, const uint32_t KT2)
+{
+    constexpr int NPW = (R + 3) / 4;
+    constexpr int PS = 32 * rpad_for(R);
+    uint32_t c[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[r] = s.c[r];
+    uint32_t diag = s.diag;
+    const int vA = half_of<0>(v2), vB = half_of<1>(v2);
+    int keyA = 0xFFFF, keyB = 0xFFFF;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t top = k == 0 ? s.top[0] : k == 1 ? s.top[1] : k == 2 ? s.top[2] : s.top[3];
+        const uint32_t la = (lettersA4 >> (8 * k)) & 0xffu, lb = (lettersB4 >> (8 * k)) & 0xffu;
+        uint32_t pa[NPW], pb[NPW];
+#pragma unroll
+        for (int q = 0; q < NPW; ++q) { pa[q] = lds_u32(sprofA + la * PS + 4 * q); pb[q] = lds_u32(sprofB + lb * PS + 4 * q); }
+        sw16_column_plain<R>(c, top, diag, pa, pb, KL2, KT2);
+        diag = top;
+#pragma unroll
+        for (int r = R - 1; r >= 0; --r) {
+            if (half_of<0>(c[r]) == vA) keyA = min(keyA, 4 * r + k);
+            if (half_of<1>(c[r]) == vB) keyB = min(keyB, 4 * r + k);
+        }
+    }
+    return (uint32_t)keyA | ((uint32_t)keyB << 16);
+}
+
+// bytes of one warp's shared-memory area (two profiles, the shared sentinel row, two padded texts)
+__host__ __device__ constexpr uint32_t sw16_text_bytes(uint32_t max_n) { return (max_n + 80u + 15u) & ~15u; }
+__host__ __device__ constexpr uint32_t sw16_warp_bytes(int R, int alpha, uint32_t max_n)
+{
+    return (uint32_t)(2 * alpha + 1) * 32u * (uint32_t)rpad_for(R) + 2u * sw16_text_bytes(max_n);
+}
+
+template <int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs A)
+{
+    static_assert(R % 2 == 0, "R must be even");
+    constexpr int CB = cb16_for(R);
+    constexpr int NW = R * CB / 8;          // words per store block (each word: 8 cells x 2 pairs)
+    constexpr int RPAD = rpad_for(R);
+    constexpr int PS = 32 * RPAD;
+    constexpr int NPW = (R + 3) / 4;
+    constexpr int TPAD = 32;                // sentinel letters in front of the text
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane;
+    const int alpha = A.alpha;
+    const uint32_t textBytes = sw16_text_bytes(A.max_n);
+    const uint32_t warpBytes = sw16_warp_bytes(R, alpha, A.max_n);
+
+    int8_t *S4s = reinterpret_cast<int8_t *>(smem);
+    unsigned char *wbase = smem + 32 * MAX_ALPHA + (size_t)warp * warpBytes;
+    unsigned char *profA = wbase, *profB = profA + alpha * PS, *sent = profB + alpha * PS;
+    unsigned char *textA = sent + PS, *textB = textA + textBytes;
+    const uint32_t sentA = 2 * alpha, sentB = alpha;          // letter whose row is the sentinel, relative to each profile
+    const uint32_t sprofA = (uint32_t)__cvta_generic_to_shared(profA) + l * RPAD, sprofB = sprofA + alpha * PS;
+    const uint32_t stextA = (uint32_t)__cvta_generic_to_shared(textA), stextB = stextA + textBytes;
+
+    for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
+    for (int i = lane; i < PS / 4; i += 32) reinterpret_cast<uint32_t *>(sent)[i] = 0x80808080u;
+    __syncthreads();
+
+    const int KL = 2 - SCALE * A.gap, KT = 1 - SCALE * A.gap;
+    const uint32_t KL2 = (uint32_t)(KL & 0xffff) * 0x10001u, KT2 = (uint32_t)(KT & 0xffff) * 0x10001u;
+    const uint32_t first_pos = A.dyn->first, n_pos = A.dyn->count;
+    uint32_t *const dirs = A.dirs + A.dyn->dir_base;
+    const uint32_t nTasks = (n_pos + 1) / 2;
+    const int phase = (TPAD - l) & 3;                 // byte phase of the lane's column inside a text word
+    const int word0 = (TPAD - l) >> 2;                // word that holds the lane's column at step 0
+
+    for (uint32_t task = blockIdx.x * WARPS + warp; task < nTasks; task += gridDim.x * WARPS) {
+        const uint32_t posA = task * 2, posB = posA + 1;
+        const bool validB = posB < n_pos;
+        uint32_t pairA = 0, pairB = 0; int nA = 0, mA = 0, nB = 0, mB = 0;
+        const uint8_t *txA = nullptr, *ptA = nullptr, *txB = nullptr, *ptB = nullptr;
+        {
+            pairA = A.order[first_pos + posA];
+            const int64_t t0 = A.text_off[pairA], p0 = A.pattern_off[pairA];
+            nA = (int)(A.text_off[pairA + 1] - t0); mA = (int)(A.pattern_off[pairA + 1] - p0);
+            txA = A.text + t0; ptA = A.pattern + p0;
+        }
+        if (validB) {
+            pairB = A.order[first_pos + posB];
+            const int64_t t0 = A.text_off[pairB], p0 = A.pattern_off[pairB];
+            nB = (int)(A.text_off[pairB + 1] - t0); mB = (int)(A.pattern_off[pairB + 1] - p0);
+            txB = A.text + t0; ptB = A.pattern + p0;
+        }
+        __syncwarp();
+        const int nG = max(nA, nB);
+        const int nSteps = nG + 31;
+        const int nQuads = (nSteps + 3) >> 2;
+        // texts: TPAD sentinels, the letters, sentinels up to the last byte any quad can touch
+        for (int j = l; j < 4 * nQuads + TPAD + 8; j += 32) {
+            const int t = j - TPAD;
+            textA[j] = (t >= 0 && t < nA) ? (unsigned char)min((int)txA[t], alpha - 1) : (unsigned char)sentA;
+            textB[j] = (t >= 0 && t < nB) ? (unsigned char)min((int)txB[t], alpha - 1) : (unsigned char)sentB;
+        }
+        for (int i = l; i < 32 * R; i += 32) {
+            const int off = (i / R) * RPAD + (i % R);
+            const int8_t *sa_ = i < mA ? S4s + 32 * min((int)ptA[i], alpha - 1) : nullptr;
+            const int8_t *sb_ = i < mB ? S4s + 32 * min((int)ptB[i], alpha - 1) : nullptr;
+            for (int a = 0; a < alpha; ++a) {
+                profA[a * PS + off] = sa_ ? (unsigned char)sa_[a] : (unsigned char)0x80;
+                profB[a * PS + off] = sb_ ? (unsigned char)sb_[a] : (unsigned char)0x80;
+            }
+        }
+        __syncwarp();
+
+        uint32_t c[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) c[r] = 0u;
+        uint32_t prevTop = 0u, bottom = 0u;
+        uint32_t best2 = 0u;
+        int bestqA = 0, bestqB = 0;
+        Quad16<R> snap;
+#pragma unroll
+        for (int r = 0; r < R; ++r) snap.c[r] = 0u;
+        snap.top[0] = snap.top[1] = snap.top[2] = snap.top[3] = 0u; snap.diag = 0u;
+
+        uint32_t *dptr = dirs + (size_t)task * A.task_stride + lane;
+        const int nBlocks = (nSteps + CB - 1) / CB;
+        uint32_t pTextA = stextA + 4 * word0, pTextB = stextB + 4 * word0;
+        uint32_t wA0 = lds_u32(pTextA), wB0 = lds_u32(pTextB);
+
+        for (int q = 0; q < nQuads; ++q) {
+            pTextA += 4; pTextB += 4;
+            const uint32_t wA1 = lds_u32(pTextA), wB1 = lds_u32(pTextB);
+            const uint32_t la4 = __funnelshift_r(wA0, wA1, 8 * phase), lb4 = __funnelshift_r(wB0, wB1, 8 * phase);
+            wA0 = wA1; wB0 = wB1;
+
+            Quad16<R> cur;
+#pragma unroll
+            for (int r = 0; r < R; ++r) cur.c[r] = c[r];
+            cur.diag = prevTop;
+            uint32_t cm[4];
+            uint32_t acc[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) acc[w] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
+                const uint32_t top = (l == 0) ? 0u : up;
+                const uint32_t la = (la4 >> (8 * k)) & 0xffu, lb = (lb4 >> (8 * k)) & 0xffu;
+                const uint32_t aA = sprofA + la * PS, aB = sprofB + lb * PS;
+                uint32_t pa[NPW], pb[NPW];
+#pragma unroll
+                for (int w = 0; w < NPW; ++w) { pa[w] = lds_u32(aA + 4 * w); pb[w] = lds_u32(aB + 4 * w); }
+                uint32_t bmax[nblk_for(R)];
+                sweep_column16<R, true, NW>(c, top, prevTop, pa, pb, KL2, KT2, acc, R * (k % CB), bmax);
+                cur.top[k] = top;
+                prevTop = top;
+                bottom = c[R - 1];
+                uint32_t m = bmax[0];
+#pragma unroll
+                for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
+                cm[k] = m;
+                if ((k + 1) % CB == 0) {
+                    const int kb = (4 * q + k) / CB;
+                    if (CB == 4 || kb < nBlocks) {
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) dptr[(size_t)w * 32] = acc[w];
+                    }
+                    dptr += NW * 32;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) acc[w] = 0;
+                }
+            }
+
+            // ---- arg-max bookkeeping, once per quad
+            const uint32_t qm = __vmaxs2(__vmaxs2(cm[0], cm[1]), __vmaxs2(cm[2], cm[3]));
+            const uint32_t nb = __vmaxs2(best2, qm);
+            const uint32_t chg = nb ^ best2;
+            const uint32_t eq = qm ^ best2;
+            const bool impA = (chg & 0xffffu) != 0u, impB = (chg >> 16) != 0u;
+            // an equal maximum only matters while it is the pair-wide maximum (REDUX over the warp): the small
+            // scores in front of the alignment repeat all the time
+            const uint32_t fl2 = (uint32_t)__reduce_max_sync(0xffffffffu, (int)(nb & 0xffffu)) |
+                                 ((uint32_t)__reduce_max_sync(0xffffffffu, (int)(nb >> 16)) << 16);
+            const uint32_t te = eq | (nb ^ fl2);
+            const bool tieA = (te & 0xffffu) == 0u && (qm & 0xffffu) != 0u;
+            const bool tieB = (te >> 16) == 0u && (qm >> 16) != 0u;
+            const uint32_t sel = (impA ? 0x54u : 0x10u) | (impB ? 0x7600u : 0x3200u);
+#pragma unroll
+            for (int r = 0; r < R; ++r) snap.c[r] = __byte_perm(snap.c[r], cur.c[r], sel);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) snap.top[k] = __byte_perm(snap.top[k], cur.top[k], sel);
+            snap.diag = __byte_perm(snap.diag, cur.diag, sel);
+            bestqA = impA ? q : bestqA;
+            bestqB = impB ? q : bestqB;
+            best2 = nb;
+            if (tieA || tieB) {
+                // the same maximum again in a later quad: it only replaces the kept one if it sits in a smaller row
+                const int aA_ = 4 * bestqA - l + TPAD, aB_ = 4 * bestqB - l + TPAD;
+                const uint32_t oa4 = __funnelshift_r(lds_u32(stextA + (aA_ & ~3)), lds_u32(stextA + (aA_ & ~3) + 4), 8 * (aA_ & 3));
+                const uint32_t ob4 = __funnelshift_r(lds_u32(stextB + (aB_ & ~3)), lds_u32(stextB + (aB_ & ~3) + 4), 8 * (aB_ & 3));
+                const uint32_t kOld = replay_quad16<R>(snap, best2, oa4, ob4, sprofA, sprofB, KL2, KT2);
+                const uint32_t kNew = replay_quad16<R>(cur, best2, la4, lb4, sprofA, sprofB, KL2, KT2);
+                const bool repA = tieA && ((kNew & 0xffffu) >> 2) < ((kOld & 0xffffu) >> 2);
+                const bool repB = tieB && ((kNew >> 16) >> 2) < ((kOld >> 16) >> 2);
+                const uint32_t sel2 = (repA ? 0x54u : 0x10u) | (repB ? 0x7600u : 0x3200u);
+#pragma unroll
+                for (int r = 0; r < R; ++r) snap.c[r] = __byte_perm(snap.c[r], cur.c[r], sel2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) snap.top[k] = __byte_perm(snap.top[k], cur.top[k], sel2);
+                snap.diag = __byte_perm(snap.diag, cur.diag, sel2);
+                bestqA = repA ? q : bestqA;
+                bestqB = repB ? q : bestqB;
+            }
+        }
+
+        // ---- locate the first maximum inside each lane's kept quad, then reduce over the lanes
+        {
+            const int aA_ = 4 * bestqA - l + TPAD, aB_ = 4 * bestqB - l + TPAD;
+            const uint32_t oa4 = __funnelshift_r(lds_u32(stextA + (aA_ & ~3)), lds_u32(stextA + (aA_ & ~3) + 4), 8 * (aA_ & 3));
+            const uint32_t ob4 = __funnelshift_r(lds_u32(stextB + (aB_ & ~3)), lds_u32(stextB + (aB_ & ~3) + 4), 8 * (aB_ & 3));
+            const uint32_t key = replay_quad16<R>(snap, best2, oa4, ob4, sprofA, sprofB, KL2, KT2);
+            const int keyA = (int)(key & 0xffffu), keyB = (int)(key >> 16);
+            int bestvA = half_of<0>(best2), bestvB = half_of<1>(best2);
+            int bestiA = l * R + (keyA >> 2) + 1, bestjA = 4 * bestqA + (keyA & 3) - l + 1;
+            int bestiB = l * R + (keyB >> 2) + 1, bestjB = 4 * bestqB + (keyB & 3) - l + 1;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                int ov = __shfl_xor_sync(0xffffffffu, bestvA, o), oi = __shfl_xor_sync(0xffffffffu, bestiA, o),
+                    oj = __shfl_xor_sync(0xffffffffu, bestjA, o);
+                if (ov > bestvA || (ov == bestvA && (oi < bestiA || (oi == bestiA && oj < bestjA)))) { bestvA = ov; bestiA = oi; bestjA = oj; }
+                ov = __shfl_xor_sync(0xffffffffu, bestvB, o); oi = __shfl_xor_sync(0xffffffffu, bestiB, o);
+                oj = __shfl_xor_sync(0xffffffffu, bestjB, o);
+                if (ov > bestvB || (ov == bestvB && (oi < bestiB || (oi == bestiB && oj < bestjB)))) { bestvB = ov; bestiB = oi; bestjB = oj; }
+            }
+            if (l == 0) {
+                A.score[pairA] = bestvA / SCALE; A.end_i[pairA] = bestvA > 0 ? bestiA : 0; A.end_j[pairA] = bestvA > 0 ? bestjA : 0;
+                if (validB) { A.score[pairB] = bestvB / SCALE; A.end_i[pairB] = bestvB > 0 ? bestiB : 0; A.end_j[pairB] = bestvB > 0 ? bestjB : 0; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace sa

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""bench_c5.py -- BASELINE config 5: ONE global alignment split into column slices over N GPUs.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench_c5.py [--length 1000000] [--steps 1] [--check]
+
+Workload: base = `length` letters uniform over ATCG (random.seed(777)), partner = mutate.py-style
+copy (random.seed(778)); NW, blast.txt, gap 5.  Rank k owns columns [k*W, (k+1)*W) and that slice's packed
+direction words (length 1 000 000 -> 250 GB in total, so N >= 2).  At N = 1 the same code path runs on one GPU
+for lengths whose directions fit.  Prints one JSON line on rank 0: GCUPS including traceback (barrier to
+barrier, max over ranks), per-rank fill times, and the checks that do not need the (infeasible, 1 TB)
+reference matrix: re-scoring the emitted alignment reproduces the score and the strings spell the inputs.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sequence-alignment-gpu_b200"))
+
+
+def rescore(at, ap, S, gap):
+    """Score of an emitted global alignment (numpy; property check, not the oracle)."""
+    lut = np.full(256, -1, np.int64)
+    for k, ch in enumerate(b"ATCG"):
+        lut[ch] = k
+    a, b = lut[np.frombuffer(at, np.uint8)], lut[np.frombuffer(ap, np.uint8)]
+    both = (a >= 0) & (b >= 0)
+    return int(S[b[both], a[both]].sum() - gap * int((~both).sum()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--length", type=int, default=1_000_000)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--check", action="store_true", help="also run the single-matrix path on rank 0 and compare (needs the memory)")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    import synth
+    sa = load_package()
+    from sa_b200 import strips
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_c5.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t, p = synth.synthetic_pair(args.length, 777, 778)
+    n, m = len(t), len(p)
+    blast = np.array([[5 if i == j else -4 for j in range(4)] for i in range(4)], np.int32)   # scoreMatrices/dna/blast.txt
+    c0, w = strips.slice_columns(n, world)[rank]
+    need = (w + 63) * (m + 511) / 4
+    free, _ = torch.cuda.mem_get_info()
+    if need > 0.95 * free:
+        raise SystemExit(f"rank {rank}: slice needs {need / 1e9:.1f} GB of direction words, {free / 1e9:.1f} GB free -- use more GPUs")
+    al = sa.Aligner(local_rank)
+    eng = strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, p, device=f"cuda:{local_rank}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    best = None
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer)
+        else:
+            res = strips.align_pair_strips_local([eng], m)
+        t_fill_done = None
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, eng.fill_ms or 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            allt = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(allt, tt)
+        else:
+            allt = [tt]
+        wall = max(float(x[0]) for x in allt)
+        fills = [float(x[1]) for x in allt]
+        if best is None or wall < best[0]:
+            best = (wall, fills, res)
+    wall, fills, (score, at, apat, ti, pi) = best
+    if rank == 0:
+        letters = np.frombuffer(b"ATCG", np.uint8)
+        checks = dict(rescore_equals_score=rescore(at, apat, blast.astype(np.int64), 5) == score,
+                      text_spelled=at.replace(b"-", b"") == letters[t].tobytes(),
+                      pattern_spelled=apat.replace(b"-", b"") == letters[p].tobytes(),
+                      starts=[ti, pi])
+        if args.check:
+            one = sa.Aligner(local_rank)
+            a = one.align(0, 4, blast, 5, t, p)
+            checks["equals_single_matrix_path"] = (a.score, a.aligned_text, a.aligned_pattern) == (score, at, apat)
+            one.close()
+        cells = (n + 1) * (m + 1)
+        print(json.dumps(dict(metric="GCUPS incl. traceback (config 5, column slices)", value=cells / wall / 1e9, unit="GCUPS",
+                              n_gpus=world, steps=args.steps, seconds=wall, fill_ms_per_rank=fills,
+                              fill_gcups_per_rank=[(w_ * (m + 1)) / (f * 1e6) if f else None
+                                                   for (_, w_), f in zip(strips.slice_columns(n, world), fills)],
+                              score=score, aln_len=len(at), checks=checks, dtype="int32", data="synthetic",
+                              config=dict(workload=f"c5: NW {n} x {m} DNA, blast, gap 5", slices=world,
+                                          pipeline="slices run one after the other (row-chunk overlap: next round)"))))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    al.close()
+
+
+if __name__ == "__main__":
+    main()

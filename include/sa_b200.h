@@ -124,6 +124,31 @@ int sa_align_device(sa_context *ctx, const sa_scoring *scoring,
                     char *d_aligned_text, char *d_aligned_pattern, uint64_t *d_result4,
                     void *stream);
 
+/* ---- one GLOBAL alignment split into column slices, one slice per GPU (BASELINE config 5).
+ * The reference's alignSequenceGPU cannot hold such a pair (alignSequenceGPU.cu:410-416 caps the
+ * direction matrix at one device); the slices replace that single-device matrix.
+ *
+ * sa_strip_fill: fill DP columns col0+1 .. col0+text_len for all pattern_len rows.  d_left_col /
+ * d_right_col are DEVICE arrays of pattern_len+1 int32 holding 4*H(i, col0) / 4*H(i, col0+text_len),
+ * i = 0..pattern_len (the scaled form the kernels carry); d_left_col is NULL exactly when col0 == 0.
+ * d_score (device, may be NULL) receives H(pattern_len, col0+text_len).  The slice's directions stay
+ * in the context; d_text / d_pattern must stay valid until sa_strip_traceback has run.
+ *
+ * sa_strip_traceback: the path enters the slice on its right edge at DP row start_row
+ * (pattern_len for the last slice) and is followed with the reference's rules
+ * (alignSequenceCPU.cpp:64-114) to the slice's left edge, or to the origin in the first slice.
+ * The piece is written right-aligned into d_aligned_* (capacity cap >= text_len + pattern_len);
+ * d_result4 = {piece_len, row where the path leaves the slice, text index, pattern index}.
+ * The whole alignment is the concatenation of the pieces in slice order.  Both calls are enqueued
+ * on `stream` without synchronisation. */
+int sa_strip_fill(sa_context *ctx, const sa_scoring *scoring,
+                  const uint8_t *d_text, uint64_t text_len, uint64_t col0,
+                  const uint8_t *d_pattern, uint64_t pattern_len,
+                  const int32_t *d_left_col, int32_t *d_right_col, int32_t *d_score, void *stream);
+int sa_strip_traceback(sa_context *ctx, uint64_t start_row,
+                       char *d_aligned_text, char *d_aligned_pattern, uint64_t cap,
+                       uint64_t *d_result4, void *stream);
+
 /* ---- batch of independent pairs (new surface; the reference's "batch" is a
  * loop of single calls, tests/benchmarks.cu:318-322) --------------------------
  * CSR layout: pair p's text is text[text_off[p] .. text_off[p+1]) and likewise

@@ -89,6 +89,16 @@ struct sa_context {
     Slot slot[NSLOT];
     uint32_t epoch = 0;
     size_t rowbuf_entries_valid = 0;
+    // column-slice state of sa_strip_fill, consumed by sa_strip_traceback
+    struct StripState {
+        bool valid = false;
+        int R = 0, CB = 0, alpha = 0;
+        uint32_t n_strips = 0;
+        size_t strip_stride = 0;
+        const uint8_t *d_text = nullptr, *d_pat = nullptr;
+        uint64_t n = 0, m = 0, col0 = 0;
+        char alphabet[40] = {};
+    } strip;
     sa_timing timing = {};
     // per-kernel timing: (before fill, after fill, after traceback) event triples of the last call
     std::vector<cudaEvent_t> evpool;
@@ -924,6 +934,84 @@ int sa_align_device(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text
     // misc = {len, start_text, start_pattern, argmax} then score at byte 32
     SA_TRY(cudaMemcpyAsync(d_result4, ctx->misc.p, 24, cudaMemcpyDeviceToDevice, st), SA_ERR_COPY);
     SA_TRY(cudaMemcpyAsync(d_result4 + 3, ctx->misc.as<char>() + 32, 4, cudaMemcpyDeviceToDevice, st), SA_ERR_COPY);
+    return SA_OK;
+}
+
+// --------------------------------------------------------------- column slices of one pair (multi-GPU, config 5)
+// Fill the slice [col0, col0+n) x all m rows of a GLOBAL alignment.  d_left_col / d_right_col hold 4*H(i, .)
+// for i = 0..m (the form the kernels carry); d_left_col == NULL means the slice starts at the matrix border.
+// The direction words stay in the context until the next fill; d_text / d_pattern must stay valid as well.
+int sa_strip_fill(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, uint64_t col0,
+                  const uint8_t *d_pattern, uint64_t m, const int32_t *d_left_col, int32_t *d_right_col,
+                  int32_t *d_score, void *stream)
+{
+    if (!ctx || !sc || !d_text || !d_pattern || n == 0 || m == 0) return SA_ERR_ARGUMENT;
+    if (sc->mode != SA_GLOBAL) return SA_ERR_ARGUMENT;              // the arg-max of a local alignment is not sliced (yet)
+    if ((col0 == 0) != (d_left_col == nullptr)) return SA_ERR_ARGUMENT;
+    if (col0 + n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_scoring(ctx, sc, st);
+    if (rc) return rc;
+    reset_timing(ctx);
+    ctx->timing.cells = n * m;
+    ctx->strip.valid = false;
+    LongPlan P;
+    rc = plan_long(ctx, sc, n, m, &P);
+    if (rc) return rc;
+    SA_TRY(ctx->dirs.reserve((size_t)P.n_strips * P.strip_stride * 4), SA_ERR_MEMORY);
+    const size_t rowEntries = (size_t)P.ring * P.row_stride;
+    const bool fresh = rowEntries * 8 > ctx->rowbuf.cap;
+    SA_TRY(ctx->rowbuf.reserve(rowEntries * 8), SA_ERR_MEMORY);
+    ctx->epoch = (ctx->epoch + 1) & 0x7ff;
+    if (fresh || ctx->epoch == 0) {
+        SA_TRY(cudaMemsetAsync(ctx->rowbuf.p, 0, ctx->rowbuf.cap, st), SA_ERR_LAUNCH);
+        if (ctx->epoch == 0) ctx->epoch = 1;
+    }
+    SA_TRY(ctx->misc.reserve(128), SA_ERR_MEMORY);
+    LongArgs A{};
+    A.text = d_text; A.n = (uint32_t)n; A.pattern = d_pattern; A.m = (uint32_t)m;
+    A.dirs = ctx->dirs.as<uint32_t>(); A.strip_stride = P.strip_stride;
+    A.rowbuf = ctx->rowbuf.as<unsigned long long>(); A.ring = P.ring; A.row_stride = P.row_stride;
+    A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap;
+    A.n_strips = P.n_strips; A.left_col = d_left_col; A.right_col = d_right_col; A.col0 = (uint32_t)col0;
+    A.score = d_score ? d_score : reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 32);
+    A.tag_base = (uint32_t)ctx->epoch << 21;
+    A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
+    cudaEventRecord(e0, st);
+    SA_TRY(launch_long(P.R, A, false, P.grid, P.smem, st), SA_ERR_LAUNCH);
+    cudaEventRecord(e1, st); cudaEventRecord(e2, st); cudaEventRecord(e3, st);
+    ctx->timing.kernel_launches++;
+    ctx->timing_dirty = true;
+    auto &S = ctx->strip;
+    S.R = P.R; S.CB = P.CB; S.alpha = sc->alphabet_size; S.n_strips = P.n_strips; S.strip_stride = P.strip_stride;
+    S.d_text = d_text; S.d_pat = d_pattern; S.n = n; S.m = m; S.col0 = col0;
+    std::memset(S.alphabet, 0, sizeof S.alphabet);
+    std::memcpy(S.alphabet, sc->alphabet, sc->alphabet_size + 1);
+    S.valid = true;
+    return SA_OK;
+}
+
+// Follow the path through the slice filled last: it enters on the right edge at DP row start_row.  The piece is
+// written right-aligned into d_outT / d_outP (capacity cap >= n + m); d_res4 = {len, exit_row, text index, pattern index}.
+int sa_strip_traceback(sa_context *ctx, uint64_t start_row, char *d_outT, char *d_outP, uint64_t cap, uint64_t *d_res4,
+                       void *stream)
+{
+    if (!ctx || !d_outT || !d_outP || !d_res4) return SA_ERR_ARGUMENT;
+    const auto &S = ctx->strip;
+    if (!S.valid || start_row > S.m || cap < S.n + S.m) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    StripTraceArgs T{};
+    T.text = S.d_text; T.n = (uint32_t)S.n; T.pattern = S.d_pat; T.m = (uint32_t)S.m;
+    T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = S.strip_stride;
+    T.alpha = S.alpha; T.R = S.R; T.CB = S.CB; T.col0 = (uint32_t)S.col0; T.start_row = start_row;
+    std::memcpy(T.alphabet, S.alphabet, sizeof T.alphabet);
+    T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res4;
+    strip_traceback_kernel<<<1, 32, 0, st>>>(T);
+    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    ctx->timing.kernel_launches++;
     return SA_OK;
 }
 

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                 const int gi = row0 + lane * R + r + 1;
                 if (gi <= m) A.right_col[gi] = c[r];
             }
+            if (s == 0 && lane == 0) A.right_col[0] = LOCAL ? 0 : -SCALE * A.gap * (int)(A.col0 + A.n);
         }
         if (LOCAL) {
             besti = bestv > 0 ? row0 + lane * R + snapshot_first_row<R>(snap, lane, bestv) + 1 : 0;
@@ -363,6 +364,67 @@ __global__ void long_traceback_kernel(const LongTraceArgs A)
     A.res[0] = len;
     A.res[1] = (uint64_t)(int64_t)ti;
     A.res[2] = (uint64_t)(int64_t)pi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Traceback through ONE column slice of a pair that is split over several GPUs (config 5,
+// global alignment).  The path enters the slice on its right edge at DP row start_row and is
+// followed (reference rules, alignSequenceCPU.cpp:64-114) until it reaches the slice's left edge --
+// or, in the first slice (col0 == 0), the matrix origin.  The piece is written backwards into the
+// end of the output buffers; the neighbour on the left continues from res[1].
+struct StripTraceArgs {
+    const uint8_t *text;     uint32_t n;        // the slice's letters
+    const uint8_t *pattern;  uint32_t m;
+    const uint32_t *dirs;    uint64_t strip_stride;
+    int alpha;
+    int R, CB;
+    uint32_t col0;
+    uint64_t start_row;
+    char alphabet[MAX_ALPHA + 1];
+    uint64_t cap;
+    char *out_text; char *out_pattern;
+    uint64_t *res;           // [0]=len of the piece  [1]=row where the path leaves the slice  [2],[3]= text/pattern index state
+};
+
+__global__ void strip_traceback_kernel(const StripTraceArgs A)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int NW = A.R * A.CB / 16;
+    const int ROWS = 32 * A.R;
+    int i = (int)A.start_row, j = (int)A.n;
+    const bool first = A.col0 == 0;
+    const char GAPC = A.alphabet[A.alpha];
+    char *oT = A.out_text + A.cap, *oP = A.out_pattern + A.cap;
+    uint64_t len = 0;
+    size_t cachedAddr = ~(size_t)0; uint32_t cachedWord = 0;
+    auto fetch = [&](int ii, int jj) -> int {
+        const int s = (ii - 1) / ROWS, rr = (ii - 1) % ROWS;
+        const int ll = rr / A.R, r = rr % A.R;
+        const int k = (jj - 1) + ll;
+        const int kb = k / A.CB, kk = k % A.CB;
+        const int bit = (kk * A.R + r) * 2;
+        const size_t addr = (size_t)s * A.strip_stride + (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        if (addr != cachedAddr) { cachedAddr = addr; cachedWord = A.dirs[addr]; }
+        return (cachedWord >> (bit & 31)) & 3;
+    };
+    int ti = j - 1, pi = i - 1;
+    while (j > 0 || (first && i > 0)) {
+        int tag;
+        if (j == 0) tag = TAG_TOP;
+        else if (i == 0) tag = TAG_LEFT;
+        else tag = fetch(i, j);
+        const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
+        ++len;
+        oT[-(int64_t)len] = takeT ? A.alphabet[A.text[max(ti, 0)]] : GAPC;
+        oP[-(int64_t)len] = takeP ? A.alphabet[A.pattern[max(pi, 0)]] : GAPC;
+        ti -= (int)takeT;
+        pi -= (int)takeP;
+        i -= takeP; j -= takeT;
+    }
+    A.res[0] = len;
+    A.res[1] = (uint64_t)i;
+    A.res[2] = (uint64_t)(int64_t)max(ti, 0);
+    A.res[3] = (uint64_t)(int64_t)max(pi, 0);
 }
 
 } // namespace sa

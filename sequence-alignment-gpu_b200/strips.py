@@ -1,0 +1,133 @@
+"""One GLOBAL alignment split into column slices over several GPUs (BASELINE config 5).
+
+Rank k owns the text columns [k*W, (k+1)*W), W = ceil(n / world), all pattern rows, and the packed
+direction words of that slice (a 1 M x 1 M pair needs 250 GB of directions: 125 GB per GPU at N = 2).
+
+  fill       rank k receives 4*H(., col0) -- the right-most column of rank k-1, m+1 int32 -- fills its
+             slice (sa_strip_fill) and sends its own right-most column to rank k+1.
+  traceback  walks right to left: the last rank starts at row m on its right edge, follows the path to
+             its left edge (sa_strip_traceback) and hands the row to the rank on its left.
+  result     the aligned strings are the concatenation of the pieces in rank order.
+
+The only communication is point-to-point between neighbours (torch.distributed send/recv: NCCL over
+NVLink between GPUs, gloo in the CPU tests).  The slices of this version run one after the other (a
+rank starts when the whole column of its left neighbour has arrived); overlapping them by handing the
+column over in row chunks is the planned next step.
+
+`engine` is anything with fill(left_col) -> right_col, score(), traceback(start_row): GpuStripEngine
+below for the product path; the CPU tests plug in a numpy restatement.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slice_columns(n: int, world: int):
+    """[(col0, width)] of every rank; trailing ranks may get an empty slice when n < world."""
+    W = (n + world - 1) // world
+    out = []
+    for k in range(world):
+        c0 = min(k * W, n)
+        out.append((c0, min(W, n - c0)))
+    return out
+
+
+class GpuStripEngine:
+    """One column slice on one GPU through the C ABI (torch only provides device memory and the stream)."""
+
+    def __init__(self, aligner, alpha, matrix, gap, text_slice, col0, pattern, device="cuda:0", alphabet=None):
+        import torch
+        self.torch = torch
+        self.al, self.alpha, self.matrix, self.gap, self.alphabet = aligner, alpha, matrix, gap, alphabet
+        self.dev = torch.device(device)
+        self.n, self.m, self.col0 = len(text_slice), len(pattern), int(col0)
+        self.d_text = torch.from_numpy(np.ascontiguousarray(text_slice, dtype=np.uint8)).to(self.dev)
+        self.d_pat = torch.from_numpy(np.ascontiguousarray(pattern, dtype=np.uint8)).to(self.dev)
+        self.d_score = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.fill_ms = None
+
+    def column_buffer(self):
+        return self.torch.empty(self.m + 1, dtype=self.torch.int32, device=self.dev)
+
+    def fill(self, left_col):
+        torch = self.torch
+        right = self.column_buffer()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.stream):
+            e0.record()
+            self.al.strip_fill(self.alpha, self.matrix, self.gap, self.d_text.data_ptr(), self.n, self.col0,
+                               self.d_pat.data_ptr(), self.m, left_col.data_ptr() if left_col is not None else 0,
+                               right.data_ptr(), self.d_score.data_ptr(), stream=self.stream.cuda_stream,
+                               alphabet=self.alphabet)
+            e1.record()
+        self.stream.synchronize()
+        self.fill_ms = e0.elapsed_time(e1)
+        self._keep = left_col
+        return right
+
+    def score(self):
+        return int(self.d_score.item())
+
+    def traceback(self, start_row):
+        torch = self.torch
+        cap = self.n + self.m
+        oT = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+        oP = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+        res = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.al.strip_traceback(start_row, oT.data_ptr(), oP.data_ptr(), cap, res.data_ptr(),
+                                    stream=self.stream.cuda_stream)
+        self.stream.synchronize()
+        ln, exit_row, ti, pi = (int(x) for x in res.tolist())
+        return (oT[cap - ln:].cpu().numpy().tobytes(), oP[cap - ln:].cpu().numpy().tobytes(), exit_row, ti, pi)
+
+
+def align_pair_strips_local(engines, m):
+    """All slices in ONE process (any number of slices on one GPU): the same hand-offs without a network."""
+    col = None
+    for e in engines:
+        col = e.fill(col) if e.n > 0 else col
+    live = [e for e in engines if e.n > 0]
+    score = live[-1].score()
+    row, pieces, ti, pi = m, [], 0, 0
+    for e in reversed(live):
+        t, p, row, ti, pi = e.traceback(row)
+        pieces.append((t, p))
+    pieces.reverse()
+    return score, b"".join(t for t, _ in pieces), b"".join(p for _, p in pieces), ti, pi
+
+
+def align_pair_strips(engine, m, rank: int, world: int, make_column, group=None):
+    """One slice per rank.  `make_column()` returns an empty (m+1) int32 tensor on the device the
+    process group communicates on.  Returns (score, aligned_text, aligned_pattern, text_idx, pattern_idx)
+    on every rank."""
+    import torch
+    import torch.distributed as dist
+    left = None
+    if rank > 0:
+        left = make_column()
+        dist.recv(left, src=rank - 1, group=group)
+    right = engine.fill(left) if engine.n > 0 else left
+    if rank + 1 < world:
+        dist.send(right, dst=rank + 1, group=group)
+    # score of the whole pair: known on the last rank that owns columns
+    row_t = torch.zeros(1, dtype=torch.int64, device=right.device)
+    if rank + 1 < world:
+        dist.recv(row_t, src=rank + 1, group=group)
+        row = int(row_t.item())
+    else:
+        row = m
+    if engine.n > 0:
+        t, p, row, ti, pi = engine.traceback(row)
+        score = engine.score()
+    else:
+        t, p, ti, pi, score = b"", b"", 0, 0, None
+    if rank > 0:
+        row_t.fill_(row)
+        dist.send(row_t, dst=rank - 1, group=group)
+    parts = [None] * world
+    dist.all_gather_object(parts, (t, p, ti, pi, score), group=group)
+    score = [x[4] for x in parts if x[4] is not None][-1]
+    return (score, b"".join(x[0] for x in parts), b"".join(x[1] for x in parts), parts[0][2], parts[0][3])

@@ -94,3 +94,47 @@ def random_case(rng, alpha, n_max=200, m_max=None, similar=True):
     if len(p) > len(t):
         t, p = p, t
     return t, p
+
+
+class NumpyStripEngine:
+    """CPU stand-in for GpuStripEngine (test infrastructure): one column slice of a global alignment,
+    restating alignSequenceCPU.cpp:232-277 (fill: DIAG only on a strict win, gap tie -> LEFT) and :64-114
+    (traceback) on the slice.  Columns travel as 4*H like on the device."""
+
+    def __init__(self, matrix, gap, text_slice, col0, pattern, alphabet):
+        import torch
+        self.torch = torch
+        self.S, self.g = np.asarray(matrix, np.int64), int(gap)
+        self.t, self.p = np.asarray(text_slice, np.int64), np.asarray(pattern, np.int64)
+        self.n, self.m, self.col0, self.alphabet = len(self.t), len(self.p), int(col0), alphabet
+
+    def fill(self, left_col):
+        n, m, g = self.n, self.m, self.g
+        H = np.zeros((m + 1, n + 1), np.int64)
+        D = np.zeros((m + 1, n + 1), np.int8)      # 0 diag, 1 top, 2 left
+        H[:, 0] = -g * np.arange(m + 1) if left_col is None else np.asarray(left_col.numpy(), np.int64) // 4
+        H[0, :] = -g * (self.col0 + np.arange(n + 1))
+        for i in range(1, m + 1):
+            for j in range(1, n + 1):
+                left, top, diag = H[i, j - 1] - g, H[i - 1, j] - g, H[i - 1, j - 1] + self.S[self.p[i - 1], self.t[j - 1]]
+                if diag > max(left, top): H[i, j], D[i, j] = diag, 0
+                elif left >= top: H[i, j], D[i, j] = left, 2
+                else: H[i, j], D[i, j] = top, 1
+        self.H, self.D = H, D
+        return self.torch.from_numpy((4 * H[:, n]).astype(np.int32))
+
+    def score(self):
+        return int(self.H[self.m, self.n])
+
+    def traceback(self, start_row):
+        i, j = int(start_row), self.n
+        gapc = self.alphabet[len(self.alphabet) - 1:]
+        oT, oP = [], []
+        ti, pi = j - 1, i - 1
+        while j > 0 or (self.col0 == 0 and i > 0):
+            d = 1 if j == 0 else 2 if i == 0 else int(self.D[i, j])
+            takeT, takeP = d != 1, d != 2
+            oT.append(self.alphabet[self.t[ti]:self.t[ti] + 1] if takeT else gapc)
+            oP.append(self.alphabet[self.p[pi]:self.p[pi] + 1] if takeP else gapc)
+            ti -= takeT; pi -= takeP; i -= takeP; j -= takeT
+        return b"".join(reversed(oT)), b"".join(reversed(oP)), i, max(ti, 0), max(pi, 0)

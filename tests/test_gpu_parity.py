@@ -249,6 +249,50 @@ def test_full_size_c3_known_answer_and_rescore(aligner, oracle):
     assert s0 < len(t) and s1 < len(p)
 
 
+def _strip_align(sa, alpha, mat, gap, t, p, world):
+    """Column slices of one global alignment, all on cuda:0, one context per slice (strips.py)."""
+    from sa_b200 import strips
+    als = [sa.Aligner(0) for _ in range(world)]
+    try:
+        eng = [strips.GpuStripEngine(al, alpha, mat, gap, t[c0:c0 + w], c0, p)
+               for al, (c0, w) in zip(als, strips.slice_columns(len(t), world))]
+        score, at, ap, ti, pi = strips.align_pair_strips_local(eng, len(p))
+    finally:
+        for al in als:
+            al.close()
+    return sa.Alignment(score, len(at), ti, pi, at, ap)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_column_slices_vs_oracle(sa, oracle, world):
+    """BASELINE config 5 code path (sa_strip_fill / sa_strip_traceback) at sizes the oracle can check:
+    the concatenated pieces must equal the single-matrix reference result bit for bit."""
+    rng = np.random.default_rng(100 + world)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+    for alpha, mat, gap, n, m in ((4, blast, 5, 2500, 2300), (4, blast, 2, 700, 1900), (23, b62, 7, 1500, 1500),
+                                  (4, blast, 5, 9, 4), (4, blast, 5, 3000, 37)):
+        import synth
+        t = rng.integers(0, alpha, n, dtype=np.uint8)
+        base = synth.mutate_indices_numpy(t, rng, alpha)
+        p = base[:m] if m <= len(base) else np.concatenate((base, rng.integers(0, alpha, m - len(base), dtype=np.uint8)))
+        assert_same(_strip_align(sa, alpha, mat, gap, t, p, world), oracle.align(0, alpha, mat, gap, t, p), (world, alpha, n, m))
+    # low-complexity input: every tie-break rule on the slice borders
+    t = np.zeros(1200, np.uint8); p = np.zeros(1100, np.uint8); p[::9] = 1
+    assert_same(_strip_align(sa, 4, blast, 5, t, p, world), oracle.align(0, 4, blast, 5, t, p), (world, "ties"))
+
+
+def test_column_slices_full_size_c3(sa, aligner):
+    """The slice path on the 100 000 x 95 217 pair (4 slices): same answer as the single-matrix path and
+    the reference's known answer for this pair."""
+    import synth
+    t, p = synth.synthetic_pair(100000, 12345, 54321)
+    blast = helpers.matrices()["dna/blast.txt"]
+    a = _strip_align(sa, 4, blast, 5, t, p, 4)
+    assert (a.score, a.aln_len, a.start_text, a.start_pattern) == (399463, 100254, 0, 0)
+    assert_same(a, aligner.align(0, 4, blast, 5, t, p), "c3 slices vs single matrix")
+
+
 def test_full_size_c4_batch_properties(sa, aligner, oracle):
     """BASELINE config 4 shape (100 000 pairs of the 1 M recipe): every pair's alignment re-scores to its
     score, a sample is compared field by field with the oracle, s16x2 and s32 kernels agree on all pairs."""

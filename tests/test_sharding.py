@@ -73,3 +73,70 @@ def test_two_rank_gloo_sharded_batch(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert '"ok": true' in outs[0][0]
+
+
+def test_slice_columns_cover_the_text():
+    load_package()
+    from sa_b200 import strips
+    for n, w in ((10, 1), (10, 3), (7, 8), (100001, 4), (952381, 8)):
+        sl = strips.slice_columns(n, w)
+        assert len(sl) == w and sl[0][0] == 0 and sum(x[1] for x in sl) == n
+        for (a, wa), (b, _) in zip(sl, sl[1:]):
+            assert a + wa == b
+
+
+def test_strips_local_matches_oracle(oracle):
+    """Host logic of the column-slice path (strips.py) with the numpy stand-in engine: 1, 2, 3 and 5 slices."""
+    load_package()
+    from sa_b200 import strips
+    from helpers import NumpyStripEngine
+    rng = np.random.default_rng(11)
+    mat = np.full((4, 4), -4, np.int32); np.fill_diagonal(mat, 5)
+    for n, m in ((57, 49), (40, 66), (5, 3)):
+        t = rng.integers(0, 4, n, dtype=np.uint8); p = t[:m].copy() if m <= n else rng.integers(0, 4, m, dtype=np.uint8)
+        p[::7] = (p[::7] + 1) % 4
+        want = oracle.align(0, 4, mat, 5, t, p)
+        for world in (1, 2, 3, 5):
+            eng = [NumpyStripEngine(mat, 5, t[c0:c0 + w], c0, p, b"ATCG-") for c0, w in strips.slice_columns(n, world)]
+            score, at, ap, ti, pi = strips.align_pair_strips_local(eng, m)
+            assert (score, len(at), ti, pi, at, ap) == want.key(), (n, m, world)
+
+
+STRIP_WORKER = textwrap.dedent("""
+    import os, sys, json
+    import numpy as np
+    import torch, torch.distributed as dist
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    from gpu_common import load_package
+    load_package()
+    from sa_b200 import strips
+    from helpers import NumpyStripEngine
+    from oracle.oracle_py import Oracle
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    n, m = 83, 77
+    t = rng.integers(0, 4, n, dtype=np.uint8); p = t[:m].copy(); p[::5] = (p[::5] + 2) % 4
+    mat = np.full((4, 4), -4, np.int32); np.fill_diagonal(mat, 5)
+    c0, w = strips.slice_columns(n, world)[rank]
+    eng = NumpyStripEngine(mat, 5, t[c0:c0 + w], c0, p, b"ATCG-")
+    got = strips.align_pair_strips(eng, m, rank, world, lambda: torch.empty(m + 1, dtype=torch.int32))
+    want = Oracle().align(0, 4, mat, 5, t, p)
+    assert (got[0], len(got[1]), got[3], got[4], got[1], got[2]) == want.key(), "slices differ from the oracle"
+    if rank == 0:
+        print(json.dumps(dict(ok=True, score=got[0])))
+    dist.barrier()
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_gloo_column_slices(tmp_path):
+    script = tmp_path / "strip_worker.py"
+    script.write_text(STRIP_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert '"ok": true' in outs[0][0]

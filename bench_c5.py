@@ -63,7 +63,7 @@ def main():
     if need > 0.95 * free:
         raise SystemExit(f"rank {rank}: slice needs {need / 1e9:.1f} GB of direction words, {free / 1e9:.1f} GB free -- use more GPUs")
     al = sa.Aligner(local_rank)
-    eng = strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, p, device=f"cuda:{local_rank}")
+    eng = strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, n, p, device=f"cuda:{local_rank}")
 
     def barrier():
         torch.cuda.synchronize()

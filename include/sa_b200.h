@@ -131,6 +131,7 @@ int sa_align_device(sa_context *ctx, const sa_scoring *scoring,
  * sa_strip_fill: fill DP columns col0+1 .. col0+text_len for all pattern_len rows.  d_left_col /
  * d_right_col are DEVICE arrays of pattern_len+1 int32 holding 4*H(i, col0) / 4*H(i, col0+text_len),
  * i = 0..pattern_len (the scaled form the kernels carry); d_left_col is NULL exactly when col0 == 0.
+ * text_total_len is the length of the whole text (it only steers the traceback's search band).
  * d_score (device, may be NULL) receives H(pattern_len, col0+text_len).  The slice's directions stay
  * in the context; d_text / d_pattern must stay valid until sa_strip_traceback has run.
  *
@@ -142,7 +143,7 @@ int sa_align_device(sa_context *ctx, const sa_scoring *scoring,
  * The whole alignment is the concatenation of the pieces in slice order.  Both calls are enqueued
  * on `stream` without synchronisation. */
 int sa_strip_fill(sa_context *ctx, const sa_scoring *scoring,
-                  const uint8_t *d_text, uint64_t text_len, uint64_t col0,
+                  const uint8_t *d_text, uint64_t text_len, uint64_t col0, uint64_t text_total_len,
                   const uint8_t *d_pattern, uint64_t pattern_len,
                   const int32_t *d_left_col, int32_t *d_right_col, int32_t *d_score, void *stream);
 int sa_strip_traceback(sa_context *ctx, uint64_t start_row,

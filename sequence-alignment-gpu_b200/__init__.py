@@ -125,7 +125,7 @@ def lib() -> C.CDLL:
                                             C.c_uint32, C.c_uint32, C.c_void_p]
         L.sa_align_device.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.sa_strip_fill.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
+        L.sa_strip_fill.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sa_strip_traceback.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.sa_partition_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
@@ -226,10 +226,10 @@ class Aligner:
                                             d_out_pattern, d_result4, C.c_void_p(stream)))
 
     # -- column slice of one global alignment (sa_strip_fill / sa_strip_traceback); raw device pointers
-    def strip_fill(self, alpha, matrix, gap, d_text, n, col0, d_pattern, m, d_left_col, d_right_col, d_score=0,
+    def strip_fill(self, alpha, matrix, gap, d_text, n, col0, n_total, d_pattern, m, d_left_col, d_right_col, d_score=0,
                    stream=0, alphabet=None):
         sc = self._scoring(0, alpha, matrix, gap, alphabet)
-        self._check(self._L.sa_strip_fill(self._ctx, C.byref(sc), d_text, n, col0, d_pattern, m,
+        self._check(self._L.sa_strip_fill(self._ctx, C.byref(sc), d_text, n, col0, n_total, d_pattern, m,
                                           C.c_void_p(d_left_col or None), C.c_void_p(d_right_col or None),
                                           C.c_void_p(d_score or None), C.c_void_p(stream)))
 

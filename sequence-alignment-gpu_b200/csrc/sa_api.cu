@@ -96,7 +96,8 @@ struct sa_context {
         uint32_t n_strips = 0;
         size_t strip_stride = 0;
         const uint8_t *d_text = nullptr, *d_pat = nullptr;
-        uint64_t n = 0, m = 0, col0 = 0;
+        uint64_t n = 0, m = 0, col0 = 0, total = 0;
+        int gap = 0;
         char alphabet[40] = {};
     } strip;
     sa_timing timing = {};
@@ -563,6 +564,66 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
     return SA_OK;
 }
 
+// Parallel traceback over the strip layout of the last fill (sa_traceback.cuh).  start_row >= 0 selects the
+// column-slice form: the path starts at (start_row, n) and, with `slice`, ends on the slice's left edge.
+int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, uint64_t m, const uint8_t *d_text,
+                               const uint8_t *d_pat, int alpha, int gap, const char *alphabet, bool local, int *d_cv,
+                               uint32_t *d_ci, uint32_t *d_cj, int32_t *d_score, char *d_outT, char *d_outP, uint64_t cap,
+                               uint64_t *d_res, bool traceback, long long start_row, bool slice, double slope, cudaStream_t st)
+{
+    {
+        TbArgs T{};
+        T.Lay.dirs = ctx->dirs.as<uint32_t>(); T.Lay.strip_stride = P.strip_stride;
+        T.Lay.R = P.R; T.Lay.CB = P.CB; T.Lay.NW = P.NW; T.Lay.ROWS = 32 * P.R;
+        T.Lay.cbShift = P.CB == 1 ? 0 : P.CB == 2 ? 1 : P.CB == 4 ? 2 : 3; T.Lay.n = (int)n; T.Lay.m = (int)m;
+        T.text = d_text; T.pattern = d_pat;
+        T.S = ctx->dS.as<int32_t>(); T.alpha = alpha; T.gap = gap; T.local = local;
+        T.n_strips = P.n_strips;
+        T.start_given = start_row >= 0 ? 1 : 0; T.start_row = (int)std::max<long long>(0, start_row); T.slice = slice ? 1 : 0;
+        int Wd = 16;
+        while (Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;          // power of two <= ROWS/2
+        if (const char *e = std::getenv("SA_TB_WD")) { const int w = std::atoi(e); if (w >= 1) Wd = w; }
+        T.Wd = Wd; T.Q = (int)((n + Wd - 1) / Wd);
+        {
+            // band of candidates around the predicted crossing: +-max(2048 columns, n/50)
+            const uint64_t half = std::max<uint64_t>(2048, n / 50);
+            int bq = (int)((half + Wd - 1) / Wd);
+            if (const char *e = std::getenv("SA_TB_BAND")) { const int b = std::atoi(e); if (b >= 1) bq = b; }
+            T.BQ = std::max(1, std::min(bq, std::max(1, T.Q / 2)));
+            T.slope = slope > 0 ? slope : local ? 1.0 : (double)n / (double)m;
+        }
+        T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
+        const size_t nq = (size_t)2 * T.BQ + 1, S = P.n_strips;
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t oSt = carve(sizeof(TbState)), oX = carve((S + 1) * 4), oLen = carve(S * 8), oDel = carve(S * 8),
+                     oMin = carve(S * 8), oOff = carve(S * 8), oFa = carve(S * nq * 4);
+        SA_TRY(ctx->tbbuf.reserve(off), SA_ERR_MEMORY);
+        char *base = ctx->tbbuf.as<char>();
+        T.st = reinterpret_cast<TbState *>(base + oSt); T.X = reinterpret_cast<int *>(base + oX);
+        T.seg_len = reinterpret_cast<unsigned long long *>(base + oLen);
+        T.seg_delta = reinterpret_cast<long long *>(base + oDel); T.seg_min = reinterpret_cast<long long *>(base + oMin);
+        T.seg_off = reinterpret_cast<unsigned long long *>(base + oOff); T.fa = reinterpret_cast<uint32_t *>(base + oFa);
+        std::memcpy(T.alphabet, alphabet, alpha + 1);
+        T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
+        tb_prepare_kernel<<<1, 32, 0, st>>>(T);
+        ctx->timing.kernel_launches++;
+        if (traceback) {
+            const long long walkers = (long long)S * (long long)nq;
+            tb_walkers_kernel<<<(unsigned)((walkers + 127) / 128), 128, 0, st>>>(T);
+            tb_resolve_kernel<<<1, 32, 0, st>>>(T);
+            tb_count_kernel<<<(unsigned)((S + 63) / 64), 64, 0, st>>>(T);
+            tb_offsets_kernel<<<1, 32, 0, st>>>(T);
+            tb_emit_kernel<<<(unsigned)((S + 63) / 64), 64, 0, st>>>(T);
+            ctx->timing.kernel_launches += 5;
+        } else {
+            SA_TRY(cudaMemsetAsync(d_res, 0, 24, st), SA_ERR_LAUNCH);
+        }
+        SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    }
+    return SA_OK;
+}
+
 // Align one long pair whose sequences are already on the device.  Results (len, starts) land
 // in ctx->misc (device) and are read back by the caller.
 int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n,
@@ -626,53 +687,9 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
         ctx->timing.kernel_launches++;
     } else {
         // parallel traceback (sa_traceback.cuh): walkers -> resolve -> count -> offsets -> emit
-        TbArgs T{};
-        T.Lay.dirs = ctx->dirs.as<uint32_t>(); T.Lay.strip_stride = P.strip_stride;
-        T.Lay.R = P.R; T.Lay.CB = P.CB; T.Lay.NW = P.NW; T.Lay.ROWS = 32 * P.R;
-        T.Lay.cbShift = P.CB == 1 ? 0 : P.CB == 2 ? 1 : P.CB == 4 ? 2 : 3; T.Lay.n = (int)n; T.Lay.m = (int)m;
-        T.text = d_text; T.pattern = d_pat;
-        T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
-        T.n_strips = P.n_strips;
-        int Wd = 16;
-        while (Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;          // power of two <= ROWS/2
-        if (const char *e = std::getenv("SA_TB_WD")) { const int w = std::atoi(e); if (w >= 1) Wd = w; }
-        T.Wd = Wd; T.Q = (int)((n + Wd - 1) / Wd);
-        {
-            // band of candidates around the predicted crossing: +-max(2048 columns, n/50)
-            const uint64_t half = std::max<uint64_t>(2048, n / 50);
-            int bq = (int)((half + Wd - 1) / Wd);
-            if (const char *e = std::getenv("SA_TB_BAND")) { const int b = std::atoi(e); if (b >= 1) bq = b; }
-            T.BQ = std::max(1, std::min(bq, std::max(1, T.Q / 2)));
-            T.slope = local ? 1.0 : (double)n / (double)m;
-        }
-        T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
-        const size_t nq = (size_t)2 * T.BQ + 1, S = P.n_strips;
-        size_t off = 0;
-        auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-        const size_t oSt = carve(sizeof(TbState)), oX = carve((S + 1) * 4), oLen = carve(S * 8), oDel = carve(S * 8),
-                     oMin = carve(S * 8), oOff = carve(S * 8), oFa = carve(S * nq * 4);
-        SA_TRY(ctx->tbbuf.reserve(off), SA_ERR_MEMORY);
-        char *base = ctx->tbbuf.as<char>();
-        T.st = reinterpret_cast<TbState *>(base + oSt); T.X = reinterpret_cast<int *>(base + oX);
-        T.seg_len = reinterpret_cast<unsigned long long *>(base + oLen);
-        T.seg_delta = reinterpret_cast<long long *>(base + oDel); T.seg_min = reinterpret_cast<long long *>(base + oMin);
-        T.seg_off = reinterpret_cast<unsigned long long *>(base + oOff); T.fa = reinterpret_cast<uint32_t *>(base + oFa);
-        std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
-        T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
-        tb_prepare_kernel<<<1, 32, 0, st>>>(T);
-        ctx->timing.kernel_launches++;
-        if (traceback) {
-            const long long walkers = (long long)S * (long long)nq;
-            tb_walkers_kernel<<<(unsigned)((walkers + 127) / 128), 128, 0, st>>>(T);
-            tb_resolve_kernel<<<1, 32, 0, st>>>(T);
-            tb_count_kernel<<<(unsigned)((S + 63) / 64), 64, 0, st>>>(T);
-            tb_offsets_kernel<<<1, 32, 0, st>>>(T);
-            tb_emit_kernel<<<(unsigned)((S + 63) / 64), 64, 0, st>>>(T);
-            ctx->timing.kernel_launches += 5;
-        } else {
-            SA_TRY(cudaMemsetAsync(d_res, 0, 24, st), SA_ERR_LAUNCH);
-        }
-        SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+        rc = enqueue_parallel_traceback(ctx, P, n, m, d_text, d_pat, sc->alphabet_size, sc->gap, sc->alphabet, local, d_cv, d_ci,
+                                        d_cj, d_score, d_outT, d_outP, cap, d_res, traceback, -1, false, 0.0, st);
+        if (rc) return rc;
     }
     cudaEventRecord(e3, st);
     ctx->timing_dirty = true;
@@ -942,13 +959,13 @@ int sa_align_device(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text
 // for i = 0..m (the form the kernels carry); d_left_col == NULL means the slice starts at the matrix border.
 // The direction words stay in the context until the next fill; d_text / d_pattern must stay valid as well.
 int sa_strip_fill(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, uint64_t col0,
-                  const uint8_t *d_pattern, uint64_t m, const int32_t *d_left_col, int32_t *d_right_col,
-                  int32_t *d_score, void *stream)
+                  uint64_t text_total, const uint8_t *d_pattern, uint64_t m, const int32_t *d_left_col,
+                  int32_t *d_right_col, int32_t *d_score, void *stream)
 {
     if (!ctx || !sc || !d_text || !d_pattern || n == 0 || m == 0) return SA_ERR_ARGUMENT;
     if (sc->mode != SA_GLOBAL) return SA_ERR_ARGUMENT;              // the arg-max of a local alignment is not sliced (yet)
     if ((col0 == 0) != (d_left_col == nullptr)) return SA_ERR_ARGUMENT;
-    if (col0 + n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64) return SA_ERR_ARGUMENT;
+    if (col0 + n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64 || text_total < col0 + n) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = upload_scoring(ctx, sc, st);
@@ -986,7 +1003,7 @@ int sa_strip_fill(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, 
     ctx->timing_dirty = true;
     auto &S = ctx->strip;
     S.R = P.R; S.CB = P.CB; S.alpha = sc->alphabet_size; S.n_strips = P.n_strips; S.strip_stride = P.strip_stride;
-    S.d_text = d_text; S.d_pat = d_pattern; S.n = n; S.m = m; S.col0 = col0;
+    S.d_text = d_text; S.d_pat = d_pattern; S.n = n; S.m = m; S.col0 = col0; S.total = text_total; S.gap = sc->gap;
     std::memset(S.alphabet, 0, sizeof S.alphabet);
     std::memcpy(S.alphabet, sc->alphabet, sc->alphabet_size + 1);
     S.valid = true;
@@ -1003,16 +1020,23 @@ int sa_strip_traceback(sa_context *ctx, uint64_t start_row, char *d_outT, char *
     if (!S.valid || start_row > S.m || cap < S.n + S.m) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
-    StripTraceArgs T{};
-    T.text = S.d_text; T.n = (uint32_t)S.n; T.pattern = S.d_pat; T.m = (uint32_t)S.m;
-    T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = S.strip_stride;
-    T.alpha = S.alpha; T.R = S.R; T.CB = S.CB; T.col0 = (uint32_t)S.col0; T.start_row = start_row;
-    std::memcpy(T.alphabet, S.alphabet, sizeof T.alphabet);
-    T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res4;
-    strip_traceback_kernel<<<1, 32, 0, st>>>(T);
-    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
-    ctx->timing.kernel_launches++;
-    return SA_OK;
+    if (const char *e = std::getenv("SA_TB"); e && !std::strcmp(e, "serial")) {
+        StripTraceArgs T{};
+        T.text = S.d_text; T.n = (uint32_t)S.n; T.pattern = S.d_pat; T.m = (uint32_t)S.m;
+        T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = S.strip_stride;
+        T.alpha = S.alpha; T.R = S.R; T.CB = S.CB; T.col0 = (uint32_t)S.col0; T.start_row = start_row;
+        std::memcpy(T.alphabet, S.alphabet, sizeof T.alphabet);
+        T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res4;
+        strip_traceback_kernel<<<1, 32, 0, st>>>(T);
+        SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+        ctx->timing.kernel_launches++;
+        return SA_OK;
+    }
+    LongPlan P{};
+    P.R = S.R; P.CB = S.CB; P.NW = S.R * S.CB / 16; P.n_strips = S.n_strips; P.strip_stride = S.strip_stride;
+    return enqueue_parallel_traceback(ctx, P, S.n, S.m, S.d_text, S.d_pat, S.alpha, S.gap, S.alphabet, false, nullptr, nullptr,
+                                      nullptr, nullptr, d_outT, d_outP, cap, d_res4, true, (long long)start_row, S.col0 > 0,
+                                      (double)S.total / (double)S.m, st);
 }
 
 // --------------------------------------------------------------- batches

@@ -36,7 +36,7 @@ struct TbState {            // device-resident scalars of one traceback
     int H0;                 // score at the start cell (true score, not scaled)
     int s0;                 // strip containing row i0
     int cut_seg;            // local: segment in which the running score reaches 0 (-1: none, runs to the border)
-    int pad;
+    int exit_row;           // column slices: DP row at which the path leaves through the slice's left edge
     unsigned long long total_len;
     unsigned long long fallbacks;   // segments resolved by the serial fallback (diagnostic)
 };
@@ -49,6 +49,9 @@ struct TbArgs {
     int Wd, Q;                       // candidate spacing and count-1 (candidates q = 0..Q)
     int BQ;                          // walkers only cover candidates within BQ of the predicted crossing
     double slope;                    // predicted columns per row along the path (n/m global, 1 local)
+    // column slice of a global alignment (sa_strip_traceback): the path starts at (start_row, n) on the right
+    // edge; with `slice` set (not the first slice) it ends on the left edge instead of running up column 0
+    int start_given, start_row, slice;
     // fill results
     const int *cand_v; const uint32_t *cand_i; const uint32_t *cand_j;
     int32_t *score;
@@ -123,10 +126,14 @@ __global__ void tb_prepare_kernel(const TbArgs A)
         H0 = bv / SCALE; i0 = (int)bi; j0 = (int)bj;
         *A.score = H0;
         A.res[3] = (uint64_t)i0 * (uint64_t)(n + 1) + (uint64_t)j0;
+    } else if (A.start_given) {
+        H0 = 0; i0 = A.start_row; j0 = n;
+        A.res[3] = 0;
     } else {
         H0 = *A.score; i0 = m; j0 = n;
         A.res[3] = 0;
     }
+    A.st->exit_row = 0;
     A.st->i0 = i0; A.st->j0 = j0; A.st->H0 = H0;
     A.st->s0 = i0 > 0 ? (i0 - 1) / A.Lay.ROWS : 0;
     A.st->cut_seg = -1;
@@ -220,6 +227,7 @@ __device__ __forceinline__ void tb_segment(const TbArgs &A, const int t)
     char *oT = A.out_text + A.cap, *oP = A.out_pattern + A.cap;
     while (true) {
         if (A.local) { if (i <= stop_row || i == 0 || j == 0) break; }
+        else if (A.slice) { if (j == 0 || (t > 0 && i <= stop_row)) break; }      // row 0 runs LEFT to the slice edge
         else if (t == 0) { if (i == 0 && j == 0) break; }
         else if (i <= stop_row) break;
         if (MODE == 1 && budget == 0) break;
@@ -243,6 +251,7 @@ __device__ __forceinline__ void tb_segment(const TbArgs &A, const int t)
         A.seg_len[t] = len;
         A.seg_delta[t] = delta;
         A.seg_min[t] = dmin;
+        if (A.slice && j == 0 && len > 0) A.st->exit_row = i;     // exactly one segment steps onto the left edge
     }
 }
 
@@ -308,6 +317,7 @@ __global__ void tb_offsets_kernel(const TbArgs A)
     A.st->cut_seg = cut;
     A.st->total_len = off;
     A.res[0] = off;
+    if (!A.local && A.start_given) { A.res[1] = (uint64_t)A.st->exit_row; A.res[2] = 0; A.res[3] = 0; return; }
     if (!A.local) { A.res[1] = 0; A.res[2] = 0; return; }      // clamped indices end at 0 (alignSequenceCPU.cpp:100-101)
     if (!haveExit) {
         // the alignment ran into the matrix border, or ended exactly on a strip line: the last

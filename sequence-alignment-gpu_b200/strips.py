@@ -35,12 +35,12 @@ def slice_columns(n: int, world: int):
 class GpuStripEngine:
     """One column slice on one GPU through the C ABI (torch only provides device memory and the stream)."""
 
-    def __init__(self, aligner, alpha, matrix, gap, text_slice, col0, pattern, device="cuda:0", alphabet=None):
+    def __init__(self, aligner, alpha, matrix, gap, text_slice, col0, n_total, pattern, device="cuda:0", alphabet=None):
         import torch
         self.torch = torch
         self.al, self.alpha, self.matrix, self.gap, self.alphabet = aligner, alpha, matrix, gap, alphabet
         self.dev = torch.device(device)
-        self.n, self.m, self.col0 = len(text_slice), len(pattern), int(col0)
+        self.n, self.m, self.col0, self.n_total = len(text_slice), len(pattern), int(col0), int(n_total)
         self.d_text = torch.from_numpy(np.ascontiguousarray(text_slice, dtype=np.uint8)).to(self.dev)
         self.d_pat = torch.from_numpy(np.ascontiguousarray(pattern, dtype=np.uint8)).to(self.dev)
         self.d_score = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -58,7 +58,7 @@ class GpuStripEngine:
         with torch.cuda.stream(self.stream):
             e0.record()
             self.al.strip_fill(self.alpha, self.matrix, self.gap, self.d_text.data_ptr(), self.n, self.col0,
-                               self.d_pat.data_ptr(), self.m, left_col.data_ptr() if left_col is not None else 0,
+                               self.n_total, self.d_pat.data_ptr(), self.m, left_col.data_ptr() if left_col is not None else 0,
                                right.data_ptr(), self.d_score.data_ptr(), stream=self.stream.cuda_stream,
                                alphabet=self.alphabet)
             e1.record()

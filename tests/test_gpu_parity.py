@@ -254,7 +254,7 @@ def _strip_align(sa, alpha, mat, gap, t, p, world):
     from sa_b200 import strips
     als = [sa.Aligner(0) for _ in range(world)]
     try:
-        eng = [strips.GpuStripEngine(al, alpha, mat, gap, t[c0:c0 + w], c0, p)
+        eng = [strips.GpuStripEngine(al, alpha, mat, gap, t[c0:c0 + w], c0, len(t), p)
                for al, (c0, w) in zip(als, strips.slice_columns(len(t), world))]
         score, at, ap, ti, pi = strips.align_pair_strips_local(eng, len(p))
     finally:
@@ -263,10 +263,13 @@ def _strip_align(sa, alpha, mat, gap, t, p, world):
     return sa.Alignment(score, len(at), ti, pi, at, ap)
 
 
+@pytest.mark.parametrize("tb", ["parallel", "serial"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-def test_column_slices_vs_oracle(sa, oracle, world):
+def test_column_slices_vs_oracle(sa, oracle, monkeypatch, world, tb):
     """BASELINE config 5 code path (sa_strip_fill / sa_strip_traceback) at sizes the oracle can check:
     the concatenated pieces must equal the single-matrix reference result bit for bit."""
+    if tb == "serial":
+        monkeypatch.setenv("SA_TB", "serial")
     rng = np.random.default_rng(100 + world)
     blast = helpers.matrices()["dna/blast.txt"]
     b62 = helpers.matrices()["protein/blosum62.txt"]

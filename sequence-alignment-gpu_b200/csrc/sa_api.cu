@@ -83,7 +83,7 @@ struct sa_context {
     // one class overlaps the body of the next
     static constexpr int NCLS_STREAMS = 4;
     cudaStream_t clsStream[NCLS_STREAMS] = {};
-    cudaEvent_t evFork = nullptr, evJoin[NCLS_STREAMS] = {};
+    cudaEvent_t evFork = nullptr, evSorted = nullptr, evJoin[NCLS_STREAMS] = {};
     DevBuf clsSnap[NCLS_STREAMS];
     PinBuf pin;
     Slot slot[NSLOT];
@@ -107,6 +107,7 @@ struct sa_context {
     bool timing_dirty = false;
     int last_cuda = 0;
     size_t dirs_budget = (size_t)8 << 30;   // bytes of direction workspace per chunk
+    int tb_blocks_per_sm = 1;               // traceback blocks per SM while the next chunk's fill shares the GPU
 };
 
 namespace {
@@ -330,7 +331,7 @@ bool sw16_exists(const BatchCfg &cfg)
 #undef X
     return false;
 }
-size_t sw16_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n) { return 32 * MAX_ALPHA + (size_t)BATCH_WARPS * sw16_warp_bytes(c.R, alpha, max_n); }
+size_t sw16_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n) { return sw16_layout(c.R, alpha, max_n, BATCH_WARPS).blockBytes; }
 cudaError_t launch_sw16(const BatchCfg &cfg, const BatchArgs &A, int grid, size_t smem, cudaStream_t st)
 {
 #define X(r) if (cfg.R == r) { batch_sw16_kernel<r, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A); return cudaGetLastError(); }
@@ -385,7 +386,8 @@ int occupancy_batch(const BatchCfg &cfg, bool local, size_t smem)
 int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_result *d_results,
                   uint64_t *d_alnoff, char *d_outT, char *d_outP, uint32_t max_n, uint32_t max_m,
                   uint32_t *d_dirs, size_t dirs_words, void *d_fill, void *d_sort, DevBuf *snapbuf, cudaStream_t st,
-                  uint32_t first, uint32_t count, cudaStream_t stTrace = nullptr, cudaEvent_t evFillDone = nullptr)
+                  uint32_t first, uint32_t count, cudaStream_t stTrace = nullptr, cudaEvent_t evFillDone = nullptr,
+                  bool tbShare = false)
 {
     const bool split = evFillDone != nullptr;      // traceback on its own stream, overlapping the next fill
     if (!split) stTrace = st;
@@ -406,26 +408,34 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     S.key = S.hist + MAX_CLASSES * SORT_BUCKETS;
     S.order = S.key + count;
     S.dyn = reinterpret_cast<BatchClassDyn *>(reinterpret_cast<char *>(S.order + count) + ((8 - ((uintptr_t)(S.order + count) & 7)) & 7));
-    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
-    cudaEventRecord(e0, st);
-    SA_TRY(cudaMemsetAsync(S.hist, 0, (size_t)MAX_CLASSES * SORT_BUCKETS * 4, st), SA_ERR_LAUNCH);
-    batch_classify_kernel<<<(count + 255) / 256, 256, 0, st>>>(S);
-    batch_scan_kernel<<<1, 1024, 0, st>>>(S);
-    batch_scatter_kernel<<<(count + 255) / 256, 256, 0, st>>>(S);
-    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
-    ctx->timing.kernel_launches += 3;
-
-    // ---- fill: one launch per class; empty classes exit at once.  With SA_BATCH_CLASS_STREAMS (default
-    // on for big chunks) the classes run concurrently on side streams (fork/join by events) ----
+    // With SA_BATCH_CLASS_STREAMS (default on for big chunks) the binning and the class kernels run on the context's
+    // HIGH-PRIORITY side streams (fork/join by events): the classes run concurrently, and none of it queues behind the
+    // traceback blocks of the previous chunk, which would otherwise hold every SM until they drain.
     const char *cse = std::getenv("SA_BATCH_CLASS_STREAMS");
     const bool forkClasses = snapbuf == &ctx->snapbuf && count >= 4096 && T.n_classes > 1 && !(cse && cse[0] == '0');
-    if (forkClasses) cudaEventRecord(ctx->evFork, st);
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
+    cudaEventRecord(e0, st);
+    cudaStream_t stSort = st;
+    if (forkClasses) {
+        cudaEventRecord(ctx->evFork, st);
+        stSort = ctx->clsStream[0];
+        cudaStreamWaitEvent(stSort, ctx->evFork, 0);
+    }
+    SA_TRY(cudaMemsetAsync(S.hist, 0, (size_t)MAX_CLASSES * SORT_BUCKETS * 4, stSort), SA_ERR_LAUNCH);
+    batch_classify_kernel<<<(count + 255) / 256, 256, 0, stSort>>>(S);
+    batch_scan_kernel<<<1, 1024, 0, stSort>>>(S);
+    batch_scatter_kernel<<<(count + 255) / 256, 256, 0, stSort>>>(S);
+    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    ctx->timing.kernel_launches += 3;
+    if (forkClasses) cudaEventRecord(ctx->evSorted, stSort);
+
+    // ---- fill: one launch per class; empty classes exit at once ----
     const cudaStream_t stMain = st;
     for (int c = 0; c < T.n_classes; ++c) {
         const int lane_ = c % sa_context::NCLS_STREAMS;
         if (forkClasses) {
             st = ctx->clsStream[lane_];
-            if (c < sa_context::NCLS_STREAMS) cudaStreamWaitEvent(st, ctx->evFork, 0);
+            if (c > 0 && c < sa_context::NCLS_STREAMS) cudaStreamWaitEvent(st, ctx->evSorted, 0);
             snapbuf = &ctx->clsSnap[lane_];
         }
         const BatchCfg cfg{T.R[c], T.L[c]};
@@ -479,7 +489,14 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     R.S = ctx->dS.as<int32_t>(); R.alpha = sc->alphabet_size; R.gap = sc->gap; R.local = local;
     std::memcpy(R.alphabet, sc->alphabet, sc->alphabet_size + 1);
     R.results = d_results; R.aln_off = d_alnoff; R.out_text = d_outT; R.out_pattern = d_outP;
-    batch_traceback_kernel<<<(count + 127) / 128, 128, 0, stTrace>>>(R);
+    // tbShare: another chunk's fill follows on the other stream -- one block per SM leaves it its three blocks per SM
+    // (the carve-out preference follows: maximum shared memory while sharing SMs with fill blocks, the default --
+    // more L1 for the scattered tag reads -- when the traceback has the GPU to itself)
+    cudaFuncSetAttribute(batch_traceback_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         tbShare ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+    const unsigned tbFull = (count + 127) / 128;
+    const unsigned tbGrid = tbShare ? std::min<unsigned>(tbFull, (unsigned)ctx->sms * ctx->tb_blocks_per_sm) : tbFull;
+    batch_traceback_kernel<<<tbGrid, 128, 0, stTrace>>>(R);
     SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
     cudaEventRecord(e3, stTrace);
     ctx->timing.kernel_launches++;
@@ -754,8 +771,13 @@ int sa_create(int device, sa_context **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SA_ERR_NO_DEVICE; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->evFill) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    for (auto &st : ctx->clsStream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    // the fill kernels of a chunk outrank the traceback of the previous chunk (which runs on ctx->stream): when both
+    // are pending the block scheduler places fill blocks first and the light traceback blocks take what is left
+    int prLeast = 0, prGreatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
+    for (auto &st : ctx->clsStream) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prGreatest);
     cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evSorted, cudaEventDisableTiming);
     for (auto &e : ctx->evJoin) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : ctx->evTrace) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &s : ctx->slot) {
@@ -763,6 +785,13 @@ int sa_create(int device, sa_context **out)
         cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     }
     if (const char *e = std::getenv("SA_DIRS_BUDGET_MB")) ctx->dirs_budget = (size_t)std::atoll(e) << 20;
+    // The small kernels that share the GPU with the fill must ask for the same (maximum) shared-memory carve-out:
+    // an SM only changes its L1/shared split when it is empty, so with their default split the fill blocks of the
+    // next chunk (74 KB each) could not join the traceback blocks of the previous one.
+    cudaFuncSetAttribute(batch_classify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(batch_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(batch_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (const char *e = std::getenv("SA_TB_BLOCKS_PER_SM")) ctx->tb_blocks_per_sm = std::max(1, std::atoi(e));
     *out = ctx;
     return SA_OK;
 }
@@ -786,6 +815,7 @@ void sa_destroy(sa_context *ctx)
     for (auto &e : ctx->evTrace) if (e) cudaEventDestroy(e);
     for (auto &st : ctx->clsStream) if (st) cudaStreamDestroy(st);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evSorted) cudaEventDestroy(ctx->evSorted);
     for (auto &e : ctx->evJoin) if (e) cudaEventDestroy(e);
     for (auto &b : ctx->clsSnap) b.release();
     for (auto &b : ctx->pdirs) b.release();
@@ -1078,7 +1108,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
         rc = enqueue_batch(ctx, sc, b, out->results, out->aln_off, out->aligned_text, out->aligned_pattern,
                            max_n, max_m, ctx->pdirs[k].as<uint32_t>(), ctx->pdirs[k].cap / 4, ctx->fill.p, ctx->psort[k].p,
                            &ctx->snapbuf, st, (uint32_t)first, count, pipeline ? ctx->stream : nullptr,
-                           pipeline ? ctx->evFill[k] : nullptr);
+                           pipeline ? ctx->evFill[k] : nullptr, pipeline && first + chunk < b->n_pairs);
         if (rc) return rc;
         if (pipeline) cudaEventRecord(ctx->evTrace[k], ctx->stream);
     }

@@ -317,15 +317,15 @@ struct BatchTraceArgs {
 
 __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceArgs A)
 {
-    // alphabet and score matrix in shared memory: per-lane indices differ, and a divergent index into
-    // the constant bank (kernel parameters) would serialise
+    // alphabet in shared memory: per-lane indices differ, and a divergent index into the constant bank
+    // (kernel parameters) would serialise.  The score matrix is read through L1 (__ldg): the block keeps
+    // its shared-memory footprint minimal so that it fits next to the fill blocks of the next chunk.
     __shared__ char alphS[MAX_ALPHA + 1];
-    __shared__ int SS[MAX_ALPHA * MAX_ALPHA];
     for (int i = threadIdx.x; i <= A.alpha; i += blockDim.x) alphS[i] = A.alphabet[i];
-    for (int i = threadIdx.x; i < A.alpha * A.alpha; i += blockDim.x) SS[i] = A.S[i];
     __syncthreads();
-    const uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gpos >= A.dyn[A.table.n_classes].first) return;
+    // grid-stride over the pairs: a pipelined chunk launches only a few blocks per SM so that the fill blocks of the
+    // next chunk fit next to them (a full grid would hold every SM until the traceback drains)
+    for (uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x; gpos < A.dyn[A.table.n_classes].first; gpos += gridDim.x * blockDim.x) {
     int cls = 0;
     while (gpos >= A.dyn[cls].first + A.dyn[cls].count) ++cls;
     const int cR = A.table.R[cls], cL = A.table.L[cls];
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
             ++len;
             const int ct = rdT.get(ti), cp = rdP.get(pi);      // ti == j-1 and pi == i-1 inside the matrix
             emit(takeT ? (unsigned)alphS[ct] : (unsigned)GAPC, takeP ? (unsigned)alphS[cp] : (unsigned)GAPC);
-            if (tag == TAG_DIAG) H -= SS[cp * A.alpha + ct]; else H += A.gap;
+            if (tag == TAG_DIAG) H -= __ldg(A.S + cp * A.alpha + ct); else H += A.gap;
             if (takeP) row_up();
             j -= takeT;
             if (i == 0 || j == 0) break;           // :45-46, before the index update
@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     res.start_pattern = (uint64_t)(int64_t)pi;
     A.results[pair] = res;
     A.aln_off[pair] = slotEnd - len;
+    }
 }
 
 } // namespace sa

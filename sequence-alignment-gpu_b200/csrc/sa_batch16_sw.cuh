@@ -96,11 +96,20 @@ __device__ __noinline__ uint32_t replay_quad16(const Quad16<R> s, const uint32_t
     return (uint32_t)keyA | ((uint32_t)keyB << 16);
 }
 
-// bytes of one warp's shared-memory area (two profiles, the shared sentinel row, two padded texts)
+// Shared-memory layout of a block: per warp two profiles (alpha rows of PS bytes each) and two padded texts; ONE
+// sentinel row (all 0x80) behind the last warp serves every warp -- its "letter" is the distance to it in rows, so
+// the warp areas are padded to a multiple of PS.  (Falls back to a sentinel row per warp when that distance does
+// not fit a byte.)  Every KB counts here: the block must leave room for the traceback blocks of the previous chunk.
 __host__ __device__ constexpr uint32_t sw16_text_bytes(uint32_t max_n) { return (max_n + 80u + 15u) & ~15u; }
-__host__ __device__ constexpr uint32_t sw16_warp_bytes(int R, int alpha, uint32_t max_n)
+struct Sw16Layout { uint32_t warpBytes, blockBytes, sharedSentinel; };
+__host__ __device__ constexpr Sw16Layout sw16_layout(int R, int alpha, uint32_t max_n, int warps)
 {
-    return (uint32_t)(2 * alpha + 1) * 32u * (uint32_t)rpad_for(R) + 2u * sw16_text_bytes(max_n);
+    const uint32_t PS = 32u * (uint32_t)rpad_for(R);
+    const uint32_t text2 = 2u * sw16_text_bytes(max_n);
+    const uint32_t wbShared = 2u * alpha * PS + (text2 + PS - 1) / PS * PS;
+    if ((uint32_t)warps * (wbShared / PS) <= 255u) return Sw16Layout{wbShared, (uint32_t)warps * wbShared + PS, 1u};
+    const uint32_t wb = (2u * alpha + 1u) * PS + text2;
+    return Sw16Layout{wb, (uint32_t)warps * wb, 0u};
 }
 
 template <int R, int WARPS>
@@ -119,18 +128,21 @@ __global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs 
     const int l = lane;
     const int alpha = A.alpha;
     const uint32_t textBytes = sw16_text_bytes(A.max_n);
-    const uint32_t warpBytes = sw16_warp_bytes(R, alpha, A.max_n);
+    const Sw16Layout lay = sw16_layout(R, alpha, A.max_n, WARPS);
 
-    int8_t *S4s = reinterpret_cast<int8_t *>(smem);
-    unsigned char *wbase = smem + 32 * MAX_ALPHA + (size_t)warp * warpBytes;
-    unsigned char *profA = wbase, *profB = profA + alpha * PS, *sent = profB + alpha * PS;
-    unsigned char *textA = sent + PS, *textB = textA + textBytes;
-    const uint32_t sentA = 2 * alpha, sentB = alpha;          // letter whose row is the sentinel, relative to each profile
+    // (the 4*S table is read from global memory / L1 while staging: shared memory is kept for profiles)
+    const int8_t *S4s = A.S4;
+    unsigned char *wbase = smem + (size_t)warp * lay.warpBytes;
+    unsigned char *profA = wbase, *profB = profA + alpha * PS;
+    unsigned char *textA = profB + alpha * PS + (lay.sharedSentinel ? 0 : PS), *textB = textA + textBytes;
+    unsigned char *sent = lay.sharedSentinel ? smem + (size_t)WARPS * lay.warpBytes : profB + alpha * PS;
+    // letter whose row is the sentinel, relative to each profile
+    const uint32_t sentA = lay.sharedSentinel ? (uint32_t)(WARPS - warp) * (lay.warpBytes / PS) : 2u * alpha, sentB = sentA - alpha;
     const uint32_t sprofA = (uint32_t)__cvta_generic_to_shared(profA) + l * RPAD, sprofB = sprofA + alpha * PS;
     const uint32_t stextA = (uint32_t)__cvta_generic_to_shared(textA), stextB = stextA + textBytes;
 
-    for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
-    for (int i = lane; i < PS / 4; i += 32) reinterpret_cast<uint32_t *>(sent)[i] = 0x80808080u;
+    if (!lay.sharedSentinel || warp == 0)
+        for (int i = lane; i < PS / 4; i += 32) reinterpret_cast<uint32_t *>(sent)[i] = 0x80808080u;
     __syncthreads();
 
     const int KL = 2 - SCALE * A.gap, KT = 1 - SCALE * A.gap;

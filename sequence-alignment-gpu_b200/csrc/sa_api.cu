@@ -332,18 +332,23 @@ bool sw16_exists(const BatchCfg &cfg)
     return false;
 }
 size_t sw16_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n) { return sw16_layout(c.R, alpha, max_n, BATCH_WARPS).blockBytes; }
-cudaError_t launch_sw16(const BatchCfg &cfg, const BatchArgs &A, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_sw16(const BatchCfg &cfg, const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
 {
-#define X(r) if (cfg.R == r) { batch_sw16_kernel<r, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A); return cudaGetLastError(); }
+#define X(r) if (cfg.R == r) { \
+        if (local) batch_line16_kernel<r, true, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A); \
+        else batch_line16_kernel<r, false, BATCH_WARPS><<<grid, BATCH_WARPS * 32, smem, st>>>(A); \
+        return cudaGetLastError(); }
     SA_SW16_R_LIST(X)
 #undef X
     return cudaErrorInvalidValue;
 }
-int occupancy_sw16(const BatchCfg &cfg, size_t smem)
+int occupancy_sw16(const BatchCfg &cfg, bool local, size_t smem)
 {
     int nb = 0;
-#define X(r) if (cfg.R == r) { cudaFuncSetAttribute(batch_sw16_kernel<r, BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, batch_sw16_kernel<r, BATCH_WARPS>, BATCH_WARPS * 32, smem); }
+#define X(r) if (cfg.R == r) { \
+        const void *fn = local ? (const void *)batch_line16_kernel<r, true, BATCH_WARPS> : (const void *)batch_line16_kernel<r, false, BATCH_WARPS>; \
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, BATCH_WARPS * 32, smem); }
     SA_SW16_R_LIST(X)
 #undef X
     return nb;
@@ -441,7 +446,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
         const BatchCfg cfg{T.R[c], T.L[c]};
         const bool packed = T.packed[c] != 0;
         const int G = (32 / cfg.L) * (packed ? 2 : 1);                  // pairs per warp task
-        const bool sw16 = packed && local && sw16_exists(cfg);
+        const bool sw16 = packed && sw16_exists(cfg) && (local || sc->gap <= 31);      // straight-line kernels (sa_batch16_sw.cuh)
         const size_t smem = sw16 ? sw16_smem_bytes(cfg, sc->alphabet_size, max_n) : batch_smem_bytes(cfg, sc->alphabet_size, max_n, local, packed);
         if (smem > (size_t)ctx->smem_optin) return SA_ERR_ARGUMENT;
         BatchArgs A{};
@@ -449,7 +454,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
         A.order = S.order; A.dyn = S.dyn + c; A.dirs = d_dirs; A.task_stride = T.stride[c];
         A.score = d_score; A.end_i = d_ei; A.end_j = d_ej;
         A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap; A.max_n = max_n;
-        int occ = sw16 ? occupancy_sw16(cfg, smem) : packed ? occupancy_batch16(cfg, local, smem) : occupancy_batch(cfg, local, smem);
+        int occ = sw16 ? occupancy_sw16(cfg, local, smem) : packed ? occupancy_batch16(cfg, local, smem) : occupancy_batch(cfg, local, smem);
         if (occ < 1) return SA_ERR_LAUNCH;
         const uint64_t nTasksMax = ((uint64_t)count + G - 1) / G;
         int grid = (int)std::min<uint64_t>((uint64_t)ctx->sms * occ, (nTasksMax + BATCH_WARPS - 1) / BATCH_WARPS);
@@ -463,7 +468,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
             }
             A.snap_ws = snapbuf->as<uint4>();
         }
-        SA_TRY(sw16 ? launch_sw16(cfg, A, grid, smem, st)
+        SA_TRY(sw16 ? launch_sw16(cfg, A, local, grid, smem, st)
                     : packed ? launch_batch_fill16(cfg, A, local, grid, smem, st) : launch_batch_fill(cfg, A, local, grid, smem, st),
                SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;

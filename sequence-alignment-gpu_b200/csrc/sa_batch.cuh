@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     const uint64_t slotEnd = (uint64_t)(t0 + p0) + (uint64_t)(n + m);
 
     int i = (int)A.end_i[pair], j = (int)A.end_j[pair];
-    int H = A.score[pair];
+    int H = A.local ? A.score[pair] : 0;           // global: accumulated along the path (the fill does not report it)
     uint64_t len = 0;
     size_t cachedAddr = ~(size_t)0; uint32_t cachedWord = 0;
 
@@ -414,7 +414,9 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
             else tag = fetch(j);
             const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
             ++len;
-            emit(takeT ? (unsigned)alphS[rdT.get(ti)] : (unsigned)GAPC, takeP ? (unsigned)alphS[rdP.get(pi)] : (unsigned)GAPC);
+            const int ct = rdT.get(ti), cp = rdP.get(pi);
+            emit(takeT ? (unsigned)alphS[ct] : (unsigned)GAPC, takeP ? (unsigned)alphS[cp] : (unsigned)GAPC);
+            H += (tag == TAG_DIAG) ? __ldg(A.S + cp * A.alpha + ct) : -A.gap;      // the path's score is H(m, n)
             ti = max(0, ti - (int)takeT);
             pi = max(0, pi - (int)takeP);
             if (takeP) row_up();
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     }
     flush();
     sa_result res;
-    res.score = A.score[pair];
+    res.score = A.local ? A.score[pair] : H;
     res.aln_len = len;
     res.start_text = (uint64_t)(int64_t)ti;
     res.start_pattern = (uint64_t)(int64_t)pi;

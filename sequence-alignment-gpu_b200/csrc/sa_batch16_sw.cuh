@@ -112,8 +112,8 @@ __host__ __device__ constexpr Sw16Layout sw16_layout(int R, int alpha, uint32_t 
     return Sw16Layout{wb, (uint32_t)warps * wb, 0u};
 }
 
-template <int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs A)
+template <int R, bool LOCAL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
     constexpr int CB = cb16_for(R);
@@ -191,10 +191,16 @@ __global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs 
         }
         __syncwarp();
 
+        // NW: a lane that has not reached its first column yet must keep its border column H(i,0) = -g*i.  Its
+        // sentinel letters take DIAG out (-128) and, while k < l, the LEFT constant is +2 instead of 2-4g: then
+        // cL = c+2 beats cT (= 4H of the row above - 4g + 1 = c+1) and the cell reproduces itself.  (g <= 31.)
         uint32_t c[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) c[r] = 0u;
-        uint32_t prevTop = 0u, bottom = 0u;
+        for (int r = 0; r < R; ++r) c[r] = LOCAL ? 0u : (uint32_t)((-SCALE * A.gap * (l * R + r + 1)) & 0xffff) * 0x10001u;
+        uint32_t prevTop = LOCAL ? 0u : (uint32_t)((-SCALE * A.gap * (l * R)) & 0xffff) * 0x10001u;
+        uint32_t bottom = c[R - 1];
+        const uint32_t G2 = (uint32_t)((SCALE * A.gap) & 0xffff) * 0x10001u;
+        uint32_t border = 0u;                         // NW: 4*H(0, column) of the step, both halves
         uint32_t best2 = 0u;
         int bestqA = 0, bestqB = 0;
         Quad16<R> snap;
@@ -224,21 +230,25 @@ __global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs 
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
-                const uint32_t top = (l == 0) ? 0u : up;
+                if (!LOCAL) border = __vsub2(border, G2);
+                const uint32_t top = (l == 0) ? (LOCAL ? 0u : border) : up;
+                const uint32_t KLk = (LOCAL || 4 * q + k >= l) ? KL2 : 0x00020002u;
                 const uint32_t la = (la4 >> (8 * k)) & 0xffu, lb = (lb4 >> (8 * k)) & 0xffu;
                 const uint32_t aA = sprofA + la * PS, aB = sprofB + lb * PS;
                 uint32_t pa[NPW], pb[NPW];
 #pragma unroll
                 for (int w = 0; w < NPW; ++w) { pa[w] = lds_u32(aA + 4 * w); pb[w] = lds_u32(aB + 4 * w); }
                 uint32_t bmax[nblk_for(R)];
-                sweep_column16<R, true, NW>(c, top, prevTop, pa, pb, KL2, KT2, acc, R * (k % CB), bmax);
+                sweep_column16<R, LOCAL, NW>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * (k % CB), bmax);
                 cur.top[k] = top;
                 prevTop = top;
                 bottom = c[R - 1];
-                uint32_t m = bmax[0];
+                if (LOCAL) {
+                    uint32_t m = bmax[0];
 #pragma unroll
-                for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
-                cm[k] = m;
+                    for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
+                    cm[k] = m;
+                }
                 if ((k + 1) % CB == 0) {
                     const int kb = (4 * q + k) / CB;
                     if (CB == 4 || kb < nBlocks) {
@@ -251,6 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs 
                 }
             }
 
+            if (!LOCAL) continue;        // global: the end cell is (m, n) and the traceback re-derives the score
             // ---- arg-max bookkeeping, once per quad
             const uint32_t qm = __vmaxs2(__vmaxs2(cm[0], cm[1]), __vmaxs2(cm[2], cm[3]));
             const uint32_t nb = __vmaxs2(best2, qm);
@@ -293,8 +304,13 @@ __global__ void __launch_bounds__(WARPS * 32) batch_sw16_kernel(const BatchArgs 
             }
         }
 
-        // ---- locate the first maximum inside each lane's kept quad, then reduce over the lanes
-        {
+        if (!LOCAL) {
+            if (l == 0) {
+                A.end_i[pairA] = mA; A.end_j[pairA] = nA;
+                if (validB) { A.end_i[pairB] = mB; A.end_j[pairB] = nB; }
+            }
+        } else {
+            // ---- locate the first maximum inside each lane's kept quad, then reduce over the lanes
             const int aA_ = 4 * bestqA - l + TPAD, aB_ = 4 * bestqB - l + TPAD;
             const uint32_t oa4 = __funnelshift_r(lds_u32(stextA + (aA_ & ~3)), lds_u32(stextA + (aA_ & ~3) + 4), 8 * (aA_ & 3));
             const uint32_t ob4 = __funnelshift_r(lds_u32(stextB + (aB_ & ~3)), lds_u32(stextB + (aB_ & ~3) + 4), 8 * (aB_ & 3));

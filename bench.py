@@ -396,7 +396,7 @@ def run_ours(args, rank, world, local_rank):
             clocks=clocks,
             roofline=dict(bound="hbm", achieved=hbm_ach, peak=pk["hbm_gbs"], unit="GB/s",
                           frac=(hbm_ach / pk["hbm_gbs"]) if hbm_ach else None, traffic=traffic,
-                          peak_source=pk["source"], kernel="batch_fill_kernel" if w["kind"] == "batch" else "long_fill_kernel",
+                          peak_source=pk["source"], kernel="batch_line16_kernel (all class launches of the step)" if w["kind"] == "batch" else "long_fill_kernel",
                           kernel_ms_per_step=fill_us / 1e3, traceback_ms_per_step=tb_us / 1e3,
                           algorithmic_bytes_per_step=alg_bytes,
                           note="HBM roofline of the packed direction matrix (0.25 B/cell); the binding roofline is DPX-ALU, see roofline_dpx"),

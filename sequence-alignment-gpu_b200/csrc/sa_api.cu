@@ -106,7 +106,11 @@ struct sa_context {
     size_t evused = 0;
     bool timing_dirty = false;
     int last_cuda = 0;
-    size_t dirs_budget = (size_t)8 << 30;   // bytes of direction workspace per chunk
+    // bytes of direction workspace per chunk.  ~2.5-3 GB (about 120 k pairs of 300 aa) is the sweet spot on B200: the
+    // scattered tag reads of the traceback start missing the TLB / L2 with larger chunks (measured 30.2 ms per
+    // 1 M pairs at 2.5 GB vs 32.5 ms at 8 GB), smaller chunks pay more launches and tails.
+    size_t dirs_budget = (size_t)3 << 30;
+    size_t host_dirs_budget = (size_t)8 << 30;    // host path: split over its NSLOT slots
     int tb_blocks_per_sm = 1;               // traceback blocks per SM while the next chunk's fill shares the GPU
 };
 
@@ -790,12 +794,14 @@ int sa_create(int device, sa_context **out)
         cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     }
     if (const char *e = std::getenv("SA_DIRS_BUDGET_MB")) ctx->dirs_budget = (size_t)std::atoll(e) << 20;
+    if (const char *e = std::getenv("SA_HOST_DIRS_BUDGET_MB")) ctx->host_dirs_budget = (size_t)std::atoll(e) << 20;
     // The small kernels that share the GPU with the fill must ask for the same (maximum) shared-memory carve-out:
     // an SM only changes its L1/shared split when it is empty, so with their default split the fill blocks of the
     // next chunk (74 KB each) could not join the traceback blocks of the previous one.
     cudaFuncSetAttribute(batch_classify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(batch_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(batch_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (const char *e = std::getenv("SA_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));
     if (const char *e = std::getenv("SA_TB_BLOCKS_PER_SM")) ctx->tb_blocks_per_sm = std::max(1, std::atoi(e));
     *out = ctx;
     return SA_OK;
@@ -1160,7 +1166,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         if (!build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), &T)) return SA_ERR_ARGUMENT;
         // chunk size: bounded by the direction budget and by ~1/8 of the batch for copy/compute overlap
         const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;
-        uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / NSLOT / perPair));
+        uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->host_dirs_budget / NSLOT / perPair));
         chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, (N + 7) / 8));
         cudaEventRecord(ctx->ev[0], ctx->stream);
         for (auto &s : ctx->slot) cudaStreamWaitEvent(s.stream, ctx->ev[0], 0);
@@ -1196,7 +1202,8 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             // members too long for the batch kernels are skipped by the device-side classifier
             // (and aligned one by one below)
             rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
-                               s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, &s.snap, s.stream, 0, (uint32_t)count);
+                               s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, &s.snap, s.stream, 0, (uint32_t)count,
+                               nullptr, nullptr, /*tbShare=*/false);      // (measured: sharing does not pay with three slots in flight)
             if (rc) return rc;
             SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);

@@ -38,6 +38,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--length", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="row chunks per slice; 1 = slices run one after the other.  (Measured: chunks do not pay with the "
+                         "present kernel -- every launch still sweeps the whole slice width serially -- see DESIGN.md 6.)")
     ap.add_argument("--check", action="store_true", help="also run the single-matrix path on rank 0 and compare (needs the memory)")
     args = ap.parse_args()
     import torch
@@ -76,10 +79,9 @@ def main():
         barrier()
         t0 = time.perf_counter()
         if world > 1:
-            res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer)
+            res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer, chunks=args.chunks)
         else:
-            res = strips.align_pair_strips_local([eng], m)
-        t_fill_done = None
+            res = strips.align_pair_strips_local([eng], m, chunks=args.chunks)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt, eng.fill_ms or 0.0], dtype=torch.float64, device=dev)
@@ -111,7 +113,9 @@ def main():
                                                    for (_, w_), f in zip(strips.slice_columns(n, world), fills)],
                               score=score, aln_len=len(at), checks=checks, dtype="int32", data="synthetic",
                               config=dict(workload=f"c5: NW {n} x {m} DNA, blast, gap 5", slices=world,
-                                          pipeline="slices run one after the other (row-chunk overlap: next round)"))))
+                                          row_chunks=args.chunks,
+                                          pipeline="rank k fills row chunk c while rank k+1 fills chunk c-1" if args.chunks > 1
+                                          else "slices run one after the other"))))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

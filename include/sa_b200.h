@@ -146,6 +146,25 @@ int sa_strip_fill(sa_context *ctx, const sa_scoring *scoring,
                   const uint8_t *d_text, uint64_t text_len, uint64_t col0, uint64_t text_total_len,
                   const uint8_t *d_pattern, uint64_t pattern_len,
                   const int32_t *d_left_col, int32_t *d_right_col, int32_t *d_score, void *stream);
+/* The same fill in ROW CHUNKS, so that neighbouring GPUs overlap: as soon as a GPU has filled rows
+ * (row0, row0+rows] of its slice it can hand that part of its right-most column over and the next GPU
+ * starts on those rows while this one continues below.
+ *   sa_strip_begin      plans the slice (strip height chosen for `chunk_rows_hint` rows in flight; 0 = all rows),
+ *                       reserves the direction words and returns the chunk height to use in *chunk_rows
+ *                       (a multiple of the strip height).
+ *   sa_strip_fill_rows  fills rows row0+1 .. row0+rows; row0 must be a multiple of *chunk_rows' strip height and so
+ *                       must rows unless the chunk ends at pattern_len.  d_left_col / d_right_col are the WHOLE
+ *                       pattern_len+1 columns (the call touches rows row0..row0+rows); d_top_row (text_len int32,
+ *                       NULL when row0 == 0) is the d_bottom_row the previous chunk produced; d_bottom_row may be
+ *                       NULL for the last chunk.
+ * sa_strip_fill is begin + one chunk covering all rows. */
+int sa_strip_begin(sa_context *ctx, const sa_scoring *scoring,
+                   const uint8_t *d_text, uint64_t text_len, uint64_t col0, uint64_t text_total_len,
+                   const uint8_t *d_pattern, uint64_t pattern_len,
+                   uint64_t chunk_rows_hint, uint64_t *chunk_rows, void *stream);
+int sa_strip_fill_rows(sa_context *ctx, uint64_t row0, uint64_t rows,
+                       const int32_t *d_left_col, int32_t *d_right_col,
+                       const int32_t *d_top_row, int32_t *d_bottom_row, int32_t *d_score, void *stream);
 int sa_strip_traceback(sa_context *ctx, uint64_t start_row,
                        char *d_aligned_text, char *d_aligned_pattern, uint64_t cap,
                        uint64_t *d_result4, void *stream);

@@ -127,6 +127,10 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sa_strip_fill.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sa_strip_begin.argtypes = [C.c_void_p, C.POINTER(_Scoring), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                     C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
+        L.sa_strip_fill_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
         L.sa_strip_traceback.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.sa_partition_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         _lib = L
@@ -232,6 +236,20 @@ class Aligner:
         self._check(self._L.sa_strip_fill(self._ctx, C.byref(sc), d_text, n, col0, n_total, d_pattern, m,
                                           C.c_void_p(d_left_col or None), C.c_void_p(d_right_col or None),
                                           C.c_void_p(d_score or None), C.c_void_p(stream)))
+
+    def strip_begin(self, alpha, matrix, gap, d_text, n, col0, n_total, d_pattern, m, chunk_rows_hint=0, stream=0, alphabet=None):
+        """Plan a slice for row-chunked filling; returns the chunk height to use (multiple of the strip height)."""
+        sc = self._scoring(0, alpha, matrix, gap, alphabet)
+        out = C.c_uint64(0)
+        self._check(self._L.sa_strip_begin(self._ctx, C.byref(sc), d_text, n, col0, n_total, d_pattern, m,
+                                           int(chunk_rows_hint), C.byref(out), C.c_void_p(stream)))
+        return int(out.value)
+
+    def strip_fill_rows(self, row0, rows, d_left_col, d_right_col, d_top_row, d_bottom_row, d_score=0, stream=0):
+        self._check(self._L.sa_strip_fill_rows(self._ctx, int(row0), int(rows), C.c_void_p(d_left_col or None),
+                                               C.c_void_p(d_right_col or None), C.c_void_p(d_top_row or None),
+                                               C.c_void_p(d_bottom_row or None), C.c_void_p(d_score or None),
+                                               C.c_void_p(stream)))
 
     def strip_traceback(self, start_row, d_out_text, d_out_pattern, cap, d_result4, stream=0):
         self._check(self._L.sa_strip_traceback(self._ctx, int(start_row), d_out_text, d_out_pattern, int(cap), d_result4,

@@ -96,7 +96,8 @@ struct sa_context {
         uint32_t n_strips = 0;
         size_t strip_stride = 0;
         const uint8_t *d_text = nullptr, *d_pat = nullptr;
-        uint64_t n = 0, m = 0, col0 = 0, total = 0;
+        uint64_t n = 0, m = 0, col0 = 0, total = 0, chunk = 0;
+        size_t row_stride = 0, smem = 0;
         int gap = 0;
         char alphabet[40] = {};
     } strip;
@@ -999,13 +1000,12 @@ int sa_align_device(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text
 // Fill the slice [col0, col0+n) x all m rows of a GLOBAL alignment.  d_left_col / d_right_col hold 4*H(i, .)
 // for i = 0..m (the form the kernels carry); d_left_col == NULL means the slice starts at the matrix border.
 // The direction words stay in the context until the next fill; d_text / d_pattern must stay valid as well.
-int sa_strip_fill(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, uint64_t col0,
-                  uint64_t text_total, const uint8_t *d_pattern, uint64_t m, const int32_t *d_left_col,
-                  int32_t *d_right_col, int32_t *d_score, void *stream)
+int sa_strip_begin(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, uint64_t col0,
+                   uint64_t text_total, const uint8_t *d_pattern, uint64_t m, uint64_t chunk_rows_hint,
+                   uint64_t *chunk_rows, void *stream)
 {
     if (!ctx || !sc || !d_text || !d_pattern || n == 0 || m == 0) return SA_ERR_ARGUMENT;
     if (sc->mode != SA_GLOBAL) return SA_ERR_ARGUMENT;              // the arg-max of a local alignment is not sliced (yet)
-    if ((col0 == 0) != (d_left_col == nullptr)) return SA_ERR_ARGUMENT;
     if (col0 + n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64 || text_total < col0 + n) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1013,42 +1013,82 @@ int sa_strip_fill(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, 
     if (rc) return rc;
     reset_timing(ctx);
     ctx->timing.cells = n * m;
-    ctx->strip.valid = false;
+    auto &S = ctx->strip;
+    S.valid = false;
+    // the strip height follows the rows that are in flight together: one chunk
+    const uint64_t hint = chunk_rows_hint == 0 || chunk_rows_hint > m ? m : chunk_rows_hint;
     LongPlan P;
-    rc = plan_long(ctx, sc, n, m, &P);
+    rc = plan_long(ctx, sc, n, hint, &P);
     if (rc) return rc;
-    SA_TRY(ctx->dirs.reserve((size_t)P.n_strips * P.strip_stride * 4), SA_ERR_MEMORY);
-    const size_t rowEntries = (size_t)P.ring * P.row_stride;
+    const uint64_t ROWS = 32ull * P.R;
+    const uint64_t chunk = hint >= m ? m : (hint + ROWS - 1) / ROWS * ROWS;
+    const uint32_t stripsTotal = (uint32_t)((m + ROWS - 1) / ROWS);
+    SA_TRY(ctx->dirs.reserve((size_t)stripsTotal * P.strip_stride * 4), SA_ERR_MEMORY);
+    SA_TRY(ctx->misc.reserve(128), SA_ERR_MEMORY);
+    S.R = P.R; S.CB = P.CB; S.alpha = sc->alphabet_size; S.n_strips = stripsTotal; S.strip_stride = P.strip_stride;
+    S.row_stride = P.row_stride; S.smem = P.smem; S.chunk = chunk;
+    S.d_text = d_text; S.d_pat = d_pattern; S.n = n; S.m = m; S.col0 = col0; S.total = text_total; S.gap = sc->gap;
+    std::memset(S.alphabet, 0, sizeof S.alphabet);
+    std::memcpy(S.alphabet, sc->alphabet, sc->alphabet_size + 1);
+    S.valid = true;
+    if (chunk_rows) *chunk_rows = chunk;
+    return SA_OK;
+}
+
+int sa_strip_fill_rows(sa_context *ctx, uint64_t row0, uint64_t rows, const int32_t *d_left_col, int32_t *d_right_col,
+                       const int32_t *d_top_row, int32_t *d_bottom_row, int32_t *d_score, void *stream)
+{
+    if (!ctx || !ctx->strip.valid || rows == 0) return SA_ERR_ARGUMENT;
+    auto &S = ctx->strip;
+    const uint64_t ROWS = 32ull * S.R;
+    const bool last = row0 + rows == S.m;
+    if (row0 + rows > S.m || row0 % ROWS != 0 || (!last && rows % ROWS != 0)) return SA_ERR_ARGUMENT;
+    if ((S.col0 == 0) != (d_left_col == nullptr)) return SA_ERR_ARGUMENT;
+    if ((row0 == 0) != (d_top_row == nullptr) || (!last && !d_bottom_row)) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t nStrips = (uint32_t)((rows + ROWS - 1) / ROWS);
+    int occ = occupancy_long(S.R, false, S.smem);
+    if (occ < 1) return SA_ERR_LAUNCH;
+    const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
+    const int grid = (int)std::min<uint64_t>(maxBlocks, (nStrips + LONG_WARPS - 1) / LONG_WARPS);
+    const uint32_t ring = (uint32_t)std::min<uint64_t>(nStrips, (uint64_t)grid * LONG_WARPS + 1);
+    const size_t rowEntries = (size_t)ring * S.row_stride;
     const bool fresh = rowEntries * 8 > ctx->rowbuf.cap;
+    if (fresh) SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);       // an earlier chunk may still use the old ring
     SA_TRY(ctx->rowbuf.reserve(rowEntries * 8), SA_ERR_MEMORY);
     ctx->epoch = (ctx->epoch + 1) & 0x7ff;
     if (fresh || ctx->epoch == 0) {
         SA_TRY(cudaMemsetAsync(ctx->rowbuf.p, 0, ctx->rowbuf.cap, st), SA_ERR_LAUNCH);
         if (ctx->epoch == 0) ctx->epoch = 1;
     }
-    SA_TRY(ctx->misc.reserve(128), SA_ERR_MEMORY);
     LongArgs A{};
-    A.text = d_text; A.n = (uint32_t)n; A.pattern = d_pattern; A.m = (uint32_t)m;
-    A.dirs = ctx->dirs.as<uint32_t>(); A.strip_stride = P.strip_stride;
-    A.rowbuf = ctx->rowbuf.as<unsigned long long>(); A.ring = P.ring; A.row_stride = P.row_stride;
-    A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap;
-    A.n_strips = P.n_strips; A.left_col = d_left_col; A.right_col = d_right_col; A.col0 = (uint32_t)col0;
+    A.text = S.d_text; A.n = (uint32_t)S.n; A.pattern = S.d_pat + row0; A.m = (uint32_t)rows;
+    A.dirs = ctx->dirs.as<uint32_t>() + (size_t)(row0 / ROWS) * S.strip_stride; A.strip_stride = S.strip_stride;
+    A.rowbuf = ctx->rowbuf.as<unsigned long long>(); A.ring = ring; A.row_stride = S.row_stride;
+    A.S4 = ctx->dS4.as<int8_t>(); A.alpha = S.alpha; A.gap = S.gap;
+    A.n_strips = nStrips; A.left_col = d_left_col ? d_left_col + row0 : nullptr;
+    A.right_col = d_right_col ? d_right_col + row0 : nullptr; A.col0 = (uint32_t)S.col0;
+    A.row_base = (uint32_t)row0; A.top_row = d_top_row; A.bottom_row = last ? nullptr : d_bottom_row;
     A.score = d_score ? d_score : reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 32);
     A.tag_base = (uint32_t)ctx->epoch << 21;
     A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
     cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
-    SA_TRY(launch_long(P.R, A, false, P.grid, P.smem, st), SA_ERR_LAUNCH);
+    SA_TRY(launch_long(S.R, A, false, grid, S.smem, st), SA_ERR_LAUNCH);
     cudaEventRecord(e1, st); cudaEventRecord(e2, st); cudaEventRecord(e3, st);
     ctx->timing.kernel_launches++;
     ctx->timing_dirty = true;
-    auto &S = ctx->strip;
-    S.R = P.R; S.CB = P.CB; S.alpha = sc->alphabet_size; S.n_strips = P.n_strips; S.strip_stride = P.strip_stride;
-    S.d_text = d_text; S.d_pat = d_pattern; S.n = n; S.m = m; S.col0 = col0; S.total = text_total; S.gap = sc->gap;
-    std::memset(S.alphabet, 0, sizeof S.alphabet);
-    std::memcpy(S.alphabet, sc->alphabet, sc->alphabet_size + 1);
-    S.valid = true;
     return SA_OK;
+}
+
+int sa_strip_fill(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, uint64_t col0,
+                  uint64_t text_total, const uint8_t *d_pattern, uint64_t m, const int32_t *d_left_col,
+                  int32_t *d_right_col, int32_t *d_score, void *stream)
+{
+    int rc = sa_strip_begin(ctx, sc, d_text, n, col0, text_total, d_pattern, m, 0, nullptr, stream);
+    if (rc) return rc;
+    return sa_strip_fill_rows(ctx, 0, m, d_left_col, d_right_col, nullptr, nullptr, d_score, stream);
 }
 
 // Follow the path through the slice filled last: it enters on the right edge at DP row start_row.  The piece is

@@ -32,6 +32,12 @@ struct LongArgs {
     const int *left_col;
     int *right_col;          // optional output: 4*H(i, last column) for i = 0..m
     uint32_t col0;           // global DP column index of the slice's column 0 (for NW borders / arg-max)
+    // Row chunks of a slice (the multi-GPU pipeline hands the border column over chunk by chunk): this launch
+    // covers DP rows row_base+1 .. row_base+m; top_row[j] = 4*H(row_base, col0+1+j) replaces the matrix border
+    // when row_base > 0, bottom_row[j] receives 4*H(row_base+m, col0+1+j) (m must then be a multiple of 32*R).
+    uint32_t row_base;
+    const int *top_row;
+    int *bottom_row;
     // results
     int32_t *score;          // NW: H(m, n) of this slice
     int *cand_v; uint32_t *cand_i; uint32_t *cand_j;   // SW: per-strip arg-max candidates
@@ -103,13 +109,13 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         for (int r = 0; r < R; ++r) {
             const int gi = row0 + lane * R + r + 1;     // DP row
             if (A.left_col) c[r] = gi <= m ? A.left_col[gi] : 0;
-            else c[r] = LOCAL ? 0 : -SCALE * A.gap * gi;
+            else c[r] = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
         }
         int prevTop;                                    // 4*H(i0-1, col0)
         {
             const int gi = row0 + lane * R;
             if (A.left_col) prevTop = gi <= m ? A.left_col[gi] : 0;
-            else prevTop = LOCAL ? 0 : -SCALE * A.gap * gi;
+            else prevTop = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
         }
         int bottom = 0;
         int bestv = 0, besti = 0, bestj = 0;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                 const int ncol = col + 4 * PB;
                 if (mine && ncol < n) nextEnt = ld_volatile_u64(rowIn + ncol);
             } else if (need) {
-                topWin[(blk & 1) * PB + (lane & 7)] = LOCAL ? 0 : -SCALE * A.gap * (col + 1 + (int)A.col0);
+                topWin[(blk & 1) * PB + (lane & 7)] = A.top_row ? A.top_row[col] : LOCAL ? 0 : -SCALE * A.gap * (col + 1 + (int)A.col0);
             }
         };
         // window upkeep that must precede the prefetch for step k1 (= k+1)
@@ -197,8 +203,9 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                 sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
                 prevTop = top;
                 bottom = c[R - 1];
-                if (hasDown && lane == 31)
-                    st_volatile_u64(rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
+                if (hasDown) {
+                    if (lane == 31) st_volatile_u64(rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
+                } else if (A.bottom_row && lane == 31) A.bottom_row[jt] = bottom;
                 if (LOCAL) {
                     const int colmax = max_of_blocks(bmax);
                     if (row0 + lane * R < m &&
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                 const int gi = row0 + lane * R + r + 1;
                 if (gi <= m) A.right_col[gi] = c[r];
             }
-            if (s == 0 && lane == 0) A.right_col[0] = LOCAL ? 0 : -SCALE * A.gap * (int)(A.col0 + A.n);
+            if (s == 0 && lane == 0 && A.row_base == 0) A.right_col[0] = LOCAL ? 0 : -SCALE * A.gap * (int)(A.col0 + A.n);
         }
         if (LOCAL) {
             besti = bestv > 0 ? row0 + lane * R + snapshot_first_row<R>(snap, lane, bestv) + 1 : 0;

@@ -10,9 +10,11 @@ direction words of that slice (a 1 M x 1 M pair needs 250 GB of directions: 125 
   result     the aligned strings are the concatenation of the pieces in rank order.
 
 The only communication is point-to-point between neighbours (torch.distributed send/recv: NCCL over
-NVLink between GPUs, gloo in the CPU tests).  The slices of this version run one after the other (a
-rank starts when the whole column of its left neighbour has arrived); overlapping them by handing the
-column over in row chunks is the planned next step.
+NVLink between GPUs, gloo in the CPU tests).  By default the slices run one after the other (a rank starts
+when the whole column of its left neighbour has arrived).  The row-chunk protocol (chunks > 1,
+sa_strip_fill_rows) hands the column over piecewise so that neighbours could overlap; it is exact and
+tested, but with the present kernel every launch sweeps the whole slice width serially, so K chunks cost
+K sweeps and it is slower -- the overlap needs the hand-off INSIDE one persistent launch.
 
 `engine` is anything with fill(left_col) -> right_col, score(), traceback(start_row): GpuStripEngine
 below for the product path; the CPU tests plug in a numpy restatement.
@@ -67,6 +69,22 @@ class GpuStripEngine:
         self._keep = left_col
         return right
 
+    # -- row-chunked filling (the multi-GPU pipeline): no host synchronisation, everything is ordered on self.stream
+    def begin(self, chunk_rows_hint):
+        self.chunk = self.al.strip_begin(self.alpha, self.matrix, self.gap, self.d_text.data_ptr(), self.n, self.col0,
+                                         self.n_total, self.d_pat.data_ptr(), self.m, chunk_rows_hint,
+                                         stream=self.stream.cuda_stream, alphabet=self.alphabet)
+        return self.chunk
+
+    def row_buffer(self):
+        return self.torch.empty(max(self.n, 1), dtype=self.torch.int32, device=self.dev)
+
+    def fill_rows(self, row0, rows, left_col, right_col, top_row, bottom_row):
+        self.al.strip_fill_rows(row0, rows, left_col.data_ptr() if left_col is not None else 0, right_col.data_ptr(),
+                                top_row.data_ptr() if top_row is not None else 0,
+                                bottom_row.data_ptr() if bottom_row is not None else 0, self.d_score.data_ptr(),
+                                stream=self.stream.cuda_stream)
+
     def score(self):
         return int(self.d_score.item())
 
@@ -84,11 +102,27 @@ class GpuStripEngine:
         return (oT[cap - ln:].cpu().numpy().tobytes(), oP[cap - ln:].cpu().numpy().tobytes(), exit_row, ti, pi)
 
 
-def align_pair_strips_local(engines, m):
-    """All slices in ONE process (any number of slices on one GPU): the same hand-offs without a network."""
+def align_pair_strips_local(engines, m, chunks: int = 1):
+    """All slices in ONE process (any number of slices on one GPU): the same hand-offs without a network.
+    chunks > 1 fills every slice in row chunks (the kernel path of the multi-GPU pipeline)."""
     col = None
     for e in engines:
-        col = e.fill(col) if e.n > 0 else col
+        if e.n == 0:
+            continue
+        if chunks <= 1:
+            col = e.fill(col)
+            continue
+        chunk = e.begin((m + chunks - 1) // chunks)
+        right, bufs, top, row0, c = e.column_buffer(), [e.row_buffer(), e.row_buffer()], None, 0, 0
+        while row0 < m:
+            rows = min(chunk, m - row0)
+            bottom = None if row0 + rows == m else bufs[c & 1]
+            e.fill_rows(row0, rows, col, right, top, bottom)
+            top, row0, c = bottom, row0 + rows, c + 1
+        if hasattr(e, "stream"):
+            e.stream.synchronize()
+        e._keep = (col, bufs)
+        col = right
     live = [e for e in engines if e.n > 0]
     score = live[-1].score()
     row, pieces, ti, pi = m, [], 0, 0
@@ -99,19 +133,51 @@ def align_pair_strips_local(engines, m):
     return score, b"".join(t for t, _ in pieces), b"".join(p for _, p in pieces), ti, pi
 
 
-def align_pair_strips(engine, m, rank: int, world: int, make_column, group=None):
+def fill_slice_pipelined(engine, m, rank: int, world: int, make_column, chunks: int, group=None):
+    """Fill this rank's slice in `chunks` row chunks: a chunk starts when that part of the left neighbour's
+    right-most column has arrived, and its own part of the right-most column is sent on at once, so that rank
+    k works on chunk c while rank k+1 works on chunk c-1.  Every operation is stream-ordered (engine.stream is
+    made current for the GPU engine); the host never waits inside the loop.  Returns the right-most column."""
+    import contextlib
+    import torch.distributed as dist
+    ctx = engine.torch.cuda.stream(engine.stream) if hasattr(engine, "stream") else contextlib.nullcontext()
+    with ctx:
+        chunk = engine.begin((m + chunks - 1) // chunks)
+        left = make_column() if rank > 0 else None
+        right = make_column()
+        rows_bufs = [engine.row_buffer(), engine.row_buffer()]
+        top, row0, c = None, 0, 0
+        while row0 < m:
+            rows = min(chunk, m - row0)
+            lo, hi = (row0 + 1 if c else 0), row0 + rows + 1           # column entries new in this chunk
+            if rank > 0:
+                dist.recv(left[lo:hi], src=rank - 1, group=group)
+            last = row0 + rows == m
+            bottom = None if last else rows_bufs[c & 1]
+            engine.fill_rows(row0, rows, left, right, top, bottom)
+            if rank + 1 < world:
+                dist.send(right[lo:hi], dst=rank + 1, group=group)
+            top, row0, c = bottom, row0 + rows, c + 1
+    engine._keep = (left, right, rows_bufs)
+    return right
+
+
+def align_pair_strips(engine, m, rank: int, world: int, make_column, group=None, chunks: int = 1):
     """One slice per rank.  `make_column()` returns an empty (m+1) int32 tensor on the device the
-    process group communicates on.  Returns (score, aligned_text, aligned_pattern, text_idx, pattern_idx)
-    on every rank."""
+    process group communicates on.  chunks > 1 overlaps the fills of neighbouring ranks (row chunks).
+    Returns (score, aligned_text, aligned_pattern, text_idx, pattern_idx) on every rank."""
     import torch
     import torch.distributed as dist
-    left = None
-    if rank > 0:
-        left = make_column()
-        dist.recv(left, src=rank - 1, group=group)
-    right = engine.fill(left) if engine.n > 0 else left
-    if rank + 1 < world:
-        dist.send(right, dst=rank + 1, group=group)
+    if chunks > 1 and min(w for _, w in slice_columns(engine.n_total, world)) > 0:
+        right = fill_slice_pipelined(engine, m, rank, world, make_column, chunks, group)
+    else:
+        left = None
+        if rank > 0:
+            left = make_column()
+            dist.recv(left, src=rank - 1, group=group)
+        right = engine.fill(left) if engine.n > 0 else left
+        if rank + 1 < world:
+            dist.send(right, dst=rank + 1, group=group)
     # score of the whole pair: known on the last rank that owns columns
     row_t = torch.zeros(1, dtype=torch.int64, device=right.device)
     if rank + 1 < world:

@@ -107,6 +107,7 @@ class NumpyStripEngine:
         self.S, self.g = np.asarray(matrix, np.int64), int(gap)
         self.t, self.p = np.asarray(text_slice, np.int64), np.asarray(pattern, np.int64)
         self.n, self.m, self.col0, self.alphabet = len(self.t), len(self.p), int(col0), alphabet
+        self.n_total = None            # set by the caller when the pipelined protocol is used
 
     def fill(self, left_col):
         n, m, g = self.n, self.m, self.g
@@ -122,6 +123,37 @@ class NumpyStripEngine:
                 else: H[i, j], D[i, j] = top, 1
         self.H, self.D = H, D
         return self.torch.from_numpy((4 * H[:, n]).astype(np.int32))
+
+    # row-chunked form (strips.fill_slice_pipelined)
+    def begin(self, chunk_rows_hint):
+        n, m, g = self.n, self.m, self.g
+        self.H = np.zeros((m + 1, n + 1), np.int64)
+        self.D = np.zeros((m + 1, n + 1), np.int8)
+        self.H[0, :] = -g * (self.col0 + np.arange(n + 1))
+        return (int(chunk_rows_hint) + 7) // 8 * 8          # pretend strips are 8 rows high
+
+    def column_buffer(self):
+        return self.torch.zeros(self.m + 1, dtype=self.torch.int32)
+
+    def row_buffer(self):
+        return self.torch.zeros(max(self.n, 1), dtype=self.torch.int32)
+
+    def fill_rows(self, row0, rows, left, right, top, bottom):
+        n, g, H, D = self.n, self.g, self.H, self.D
+        if top is not None:
+            assert np.array_equal(np.asarray(top.numpy()[:n], np.int64), 4 * H[row0, 1:]), "top row hand-over"
+        lo = row0 + 1 if row0 else 0
+        H[lo:row0 + rows + 1, 0] = (-g * np.arange(lo, row0 + rows + 1) if left is None
+                                    else np.asarray(left.numpy()[lo:row0 + rows + 1], np.int64) // 4)
+        for i in range(row0 + 1, row0 + rows + 1):
+            for j in range(1, n + 1):
+                l_, t_, d_ = H[i, j - 1] - g, H[i - 1, j] - g, H[i - 1, j - 1] + self.S[self.p[i - 1], self.t[j - 1]]
+                if d_ > max(l_, t_): H[i, j], D[i, j] = d_, 0
+                elif l_ >= t_: H[i, j], D[i, j] = l_, 2
+                else: H[i, j], D[i, j] = t_, 1
+        right[lo:row0 + rows + 1] = self.torch.from_numpy((4 * H[lo:row0 + rows + 1, n]).astype(np.int32))
+        if bottom is not None:
+            bottom[:n] = self.torch.from_numpy((4 * H[row0 + rows, 1:]).astype(np.int32))
 
     def score(self):
         return int(self.H[self.m, self.n])

@@ -249,14 +249,14 @@ def test_full_size_c3_known_answer_and_rescore(aligner, oracle):
     assert s0 < len(t) and s1 < len(p)
 
 
-def _strip_align(sa, alpha, mat, gap, t, p, world):
+def _strip_align(sa, alpha, mat, gap, t, p, world, chunks=1):
     """Column slices of one global alignment, all on cuda:0, one context per slice (strips.py)."""
     from sa_b200 import strips
     als = [sa.Aligner(0) for _ in range(world)]
     try:
         eng = [strips.GpuStripEngine(al, alpha, mat, gap, t[c0:c0 + w], c0, len(t), p)
                for al, (c0, w) in zip(als, strips.slice_columns(len(t), world))]
-        score, at, ap, ti, pi = strips.align_pair_strips_local(eng, len(p))
+        score, at, ap, ti, pi = strips.align_pair_strips_local(eng, len(p), chunks=chunks)
     finally:
         for al in als:
             al.close()
@@ -280,6 +280,9 @@ def test_column_slices_vs_oracle(sa, oracle, monkeypatch, world, tb):
         base = synth.mutate_indices_numpy(t, rng, alpha)
         p = base[:m] if m <= len(base) else np.concatenate((base, rng.integers(0, alpha, m - len(base), dtype=np.uint8)))
         assert_same(_strip_align(sa, alpha, mat, gap, t, p, world), oracle.align(0, alpha, mat, gap, t, p), (world, alpha, n, m))
+        if tb == "parallel":      # the same slices filled in row chunks (the kernel path of the multi-GPU pipeline)
+            assert_same(_strip_align(sa, alpha, mat, gap, t, p, world, chunks=3), oracle.align(0, alpha, mat, gap, t, p),
+                        (world, alpha, n, m, "row chunks"))
     # low-complexity input: every tie-break rule on the slice borders
     t = np.zeros(1200, np.uint8); p = np.zeros(1100, np.uint8); p[::9] = 1
     assert_same(_strip_align(sa, 4, blast, 5, t, p, world), oracle.align(0, 4, blast, 5, t, p), (world, "ties"))
@@ -293,6 +296,7 @@ def test_column_slices_full_size_c3(sa, aligner):
     blast = helpers.matrices()["dna/blast.txt"]
     a = _strip_align(sa, 4, blast, 5, t, p, 4)
     assert (a.score, a.aln_len, a.start_text, a.start_pattern) == (399463, 100254, 0, 0)
+    assert_same(_strip_align(sa, 4, blast, 5, t, p, 2, chunks=5), a, "c3 slices in row chunks")
     assert_same(a, aligner.align(0, 4, blast, 5, t, p), "c3 slices vs single matrix")
 
 

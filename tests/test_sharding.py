@@ -100,6 +100,9 @@ def test_strips_local_matches_oracle(oracle):
             eng = [NumpyStripEngine(mat, 5, t[c0:c0 + w], c0, p, b"ATCG-") for c0, w in strips.slice_columns(n, world)]
             score, at, ap, ti, pi = strips.align_pair_strips_local(eng, m)
             assert (score, len(at), ti, pi, at, ap) == want.key(), (n, m, world)
+            eng = [NumpyStripEngine(mat, 5, t[c0:c0 + w], c0, p, b"ATCG-") for c0, w in strips.slice_columns(n, world)]
+            score, at, ap, ti, pi = strips.align_pair_strips_local(eng, m, chunks=3)
+            assert (score, len(at), ti, pi, at, ap) == want.key(), (n, m, world, "row chunks")
 
 
 STRIP_WORKER = textwrap.dedent("""
@@ -119,10 +122,11 @@ STRIP_WORKER = textwrap.dedent("""
     t = rng.integers(0, 4, n, dtype=np.uint8); p = t[:m].copy(); p[::5] = (p[::5] + 2) % 4
     mat = np.full((4, 4), -4, np.int32); np.fill_diagonal(mat, 5)
     c0, w = strips.slice_columns(n, world)[rank]
-    eng = NumpyStripEngine(mat, 5, t[c0:c0 + w], c0, p, b"ATCG-")
-    got = strips.align_pair_strips(eng, m, rank, world, lambda: torch.empty(m + 1, dtype=torch.int32))
     want = Oracle().align(0, 4, mat, 5, t, p)
-    assert (got[0], len(got[1]), got[3], got[4], got[1], got[2]) == want.key(), "slices differ from the oracle"
+    for chunks in (1, 4):
+        eng = NumpyStripEngine(mat, 5, t[c0:c0 + w], c0, p, b"ATCG-"); eng.n_total = n
+        got = strips.align_pair_strips(eng, m, rank, world, lambda: torch.zeros(m + 1, dtype=torch.int32), chunks=chunks)
+        assert (got[0], len(got[1]), got[3], got[4], got[1], got[2]) == want.key(), "slices differ from the oracle"
     if rank == 0:
         print(json.dumps(dict(ok=True, score=got[0])))
     dist.barrier()

@@ -107,10 +107,10 @@ struct sa_context {
     size_t evused = 0;
     bool timing_dirty = false;
     int last_cuda = 0;
-    // bytes of direction workspace per chunk.  ~2.5-3 GB (about 120 k pairs of 300 aa) is the sweet spot on B200: the
-    // scattered tag reads of the traceback start missing the TLB / L2 with larger chunks (measured 30.2 ms per
-    // 1 M pairs at 2.5 GB vs 32.5 ms at 8 GB), smaller chunks pay more launches and tails.
-    size_t dirs_budget = (size_t)3 << 30;
+    // bytes of direction workspace per chunk.  About 120 k pairs of 300 aa per chunk is the sweet spot on B200
+    // (measured per 1 M pairs: 32.2 ms at 2 GB, 30.0 at 3 GB, 29.0 at 6 GB, 31.6 at 9 GB): the scattered tag reads of
+    // the traceback start missing the TLB / L2 with larger chunks, smaller chunks pay more launches and tails.
+    size_t dirs_budget = (size_t)6 << 30;
     size_t host_dirs_budget = (size_t)8 << 30;    // host path: split over its NSLOT slots
     int tb_blocks_per_sm = 1;               // traceback blocks per SM while the next chunk's fill shares the GPU
 };
@@ -192,8 +192,9 @@ bool cfg_exists(int R, int L)
     return false;
 }
 
-size_t batch_task_stride(const BatchCfg &c, uint32_t max_n, bool packed)
+size_t batch_task_stride(const BatchCfg &c, uint32_t max_n, int packed)
 {
+    if (packed == 2) return (((size_t)max_n + 31 + 3) / 4) * 32 * pq_for(c.R);       // quad layout (sa_batch16_sw.cuh)
     const int CB = packed ? cb16_for(c.R) : cb_for(c.R), NW = c.R * CB / (packed ? 8 : 16);
     const size_t nblocks = ((size_t)max_n + c.L - 1 + CB - 1) / CB;
     return nblocks * NW * 32;
@@ -220,7 +221,8 @@ bool cfg16_exists(int R, int L)
 }
 
 // Classes needed for patterns up to max_m and texts up to max_n.  Returns false if max_m is not covered.
-bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, BatchClassTable *T)
+bool sw16_exists(const BatchCfg &cfg);
+bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, bool line, BatchClassTable *T)
 {
     std::vector<BatchCfg> cfgs;
     if (const char *e = std::getenv("SA_BATCH_CLASSES")) {
@@ -242,8 +244,9 @@ bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, BatchClassT
         if (T->n_classes == MAX_CLASSES) break;
         const int k = T->n_classes++;
         T->R[k] = c.R; T->L[k] = c.L; T->max_rows[k] = (uint32_t)(c.R * c.L);
-        T->packed[k] = allow16 && cfg16_exists(c.R, c.L);
-        T->stride[k] = batch_task_stride(c, max_n, T->packed[k] != 0);
+        // 2: straight-line kernel with the quad direction layout, 1: batch_fill16_kernel, 0: s32 kernel
+        T->packed[k] = !(allow16 && cfg16_exists(c.R, c.L)) ? 0 : (line && sw16_exists(c)) ? 2 : 1;
+        T->stride[k] = batch_task_stride(c, max_n, T->packed[k]);
         if ((uint32_t)(c.R * c.L) >= max_m) break;      // larger classes cannot occur
     }
     T->max_text = BATCH_MAX_TEXT;
@@ -336,6 +339,9 @@ bool sw16_exists(const BatchCfg &cfg)
 #undef X
     return false;
 }
+// the NW form of the straight-line kernels keeps not-yet-started lanes on their border with a -128 sentinel score,
+// which needs 4*gap - 128 < 2
+bool line16_ok(const sa_scoring *sc) { return sc->mode == SA_LOCAL || sc->gap <= 31; }
 size_t sw16_smem_bytes(const BatchCfg &c, int alpha, uint32_t max_n) { return sw16_layout(c.R, alpha, max_n, BATCH_WARPS).blockBytes; }
 cudaError_t launch_sw16(const BatchCfg &cfg, const BatchArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
 {
@@ -402,7 +408,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     const bool split = evFillDone != nullptr;      // traceback on its own stream, overlapping the next fill
     if (!split) stTrace = st;
     BatchClassTable T;
-    if (max_n > BATCH_MAX_TEXT || !build_class_table(max_n, std::min(max_m, BATCH_MAX_ROWS), fits_s16(sc, max_n, max_m), &T))
+    if (max_n > BATCH_MAX_TEXT || !build_class_table(max_n, std::min(max_m, BATCH_MAX_ROWS), fits_s16(sc, max_n, max_m), line16_ok(sc), &T))
         return SA_ERR_ARGUMENT;
     if (batch_dirs_bound(T, count) > dirs_words) return SA_ERR_MEMORY;
     const bool local = sc->mode == SA_LOCAL;
@@ -451,7 +457,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
         const BatchCfg cfg{T.R[c], T.L[c]};
         const bool packed = T.packed[c] != 0;
         const int G = (32 / cfg.L) * (packed ? 2 : 1);                  // pairs per warp task
-        const bool sw16 = packed && sw16_exists(cfg) && (local || sc->gap <= 31);      // straight-line kernels (sa_batch16_sw.cuh)
+        const bool sw16 = T.packed[c] == 2;                                            // straight-line kernels (sa_batch16_sw.cuh)
         const size_t smem = sw16 ? sw16_smem_bytes(cfg, sc->alphabet_size, max_n) : batch_smem_bytes(cfg, sc->alphabet_size, max_n, local, packed);
         if (smem > (size_t)ctx->smem_optin) return SA_ERR_ARGUMENT;
         BatchArgs A{};
@@ -506,6 +512,10 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
                          tbShare ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
     const unsigned tbFull = (count + 127) / 128;
     const unsigned tbGrid = tbShare ? std::min<unsigned>(tbFull, (unsigned)ctx->sms * ctx->tb_blocks_per_sm) : tbFull;
+    static const int tbThreads = [] { const char *e = std::getenv("SA_TB_THREADS"); return e ? std::atoi(e) : 128; }();
+    if (tbShare && tbThreads != 128)
+        batch_traceback_kernel<<<std::min<unsigned>((count + tbThreads - 1) / tbThreads, (unsigned)ctx->sms * ctx->tb_blocks_per_sm), tbThreads, 0, stTrace>>>(R);
+    else
     batch_traceback_kernel<<<tbGrid, 128, 0, stTrace>>>(R);
     SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
     cudaEventRecord(e3, stTrace);
@@ -900,7 +910,7 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
         SA_TRY(cudaMemcpyAsync(d_offs, hoffs, sizeof hoffs, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
         SA_TRY(cudaStreamSynchronize(st), SA_ERR_COPY);
         BatchClassTable T;
-        if (!build_class_table((uint32_t)n, (uint32_t)m, fits_s16(sc, (uint32_t)n, (uint32_t)m), &T)) return SA_ERR_ARGUMENT;
+        if (!build_class_table((uint32_t)n, (uint32_t)m, fits_s16(sc, (uint32_t)n, (uint32_t)m), line16_ok(sc), &T)) return SA_ERR_ARGUMENT;
         SA_TRY(ctx->dirs.reserve(batch_dirs_bound(T, 1) * 4), SA_ERR_MEMORY);
         SA_TRY(ctx->fill.reserve(64), SA_ERR_MEMORY);
         SA_TRY(ctx->sortbuf.reserve(batch_sort_bytes(1)), SA_ERR_MEMORY);
@@ -1134,7 +1144,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     int rc = upload_scoring(ctx, sc, st);
     if (rc) return rc;
     BatchClassTable T;
-    if (max_n > BATCH_MAX_TEXT || max_m > BATCH_MAX_ROWS || !build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), &T))
+    if (max_n > BATCH_MAX_TEXT || max_m > BATCH_MAX_ROWS || !build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), line16_ok(sc), &T))
         return SA_ERR_ARGUMENT;
     // Chunks are software-pipelined: sort+fill of chunk c+1 runs on the caller's stream while the
     // (latency-bound) traceback of chunk c runs on the context's stream; two buffer sets.
@@ -1144,6 +1154,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     const bool pipeline = !(ps && ps[0] == '0') && b->n_pairs >= 8192;
     if (pipeline) chunk = std::min<uint64_t>(chunk, (b->n_pairs + 3) / 4);      // at least 4 chunks to overlap
     chunk = std::min<uint64_t>(chunk, b->n_pairs);
+    chunk = (b->n_pairs + (b->n_pairs + chunk - 1) / chunk - 1) / ((b->n_pairs + chunk - 1) / chunk);      // equal chunks, no stub at the end
     for (int k = 0; k < (pipeline ? 2 : 1); ++k) {
         SA_TRY(ctx->pdirs[k].reserve(batch_dirs_bound(T, chunk) * 4), SA_ERR_MEMORY);
         SA_TRY(ctx->psort[k].reserve(batch_sort_bytes(chunk)), SA_ERR_MEMORY);
@@ -1203,7 +1214,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
 
     if (max_m > 0) {
         BatchClassTable T;
-        if (!build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), &T)) return SA_ERR_ARGUMENT;
+        if (!build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), line16_ok(sc), &T)) return SA_ERR_ARGUMENT;
         // chunk size: bounded by the direction budget and by ~1/8 of the batch for copy/compute overlap
         const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;
         uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->host_dirs_budget / NSLOT / perPair));

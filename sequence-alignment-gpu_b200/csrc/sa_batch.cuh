@@ -32,7 +32,8 @@ constexpr int SORT_BUCKETS = 512;
 struct BatchClassTable {            // static description, passed by value
     int n_classes;
     int R[MAX_CLASSES], L[MAX_CLASSES];
-    int packed[MAX_CLASSES];        // 1: s16x2 kernel, two pairs per lane group (sa_batch16.cuh)
+    int packed[MAX_CLASSES];        // 1: s16x2 kernel, two pairs per lane group (sa_batch16.cuh); 2: same, straight-line
+                                    //    kernel with the quad direction layout (sa_batch16_sw.cuh)
     uint32_t max_rows[MAX_CLASSES];
     unsigned long long stride[MAX_CLASSES];     // direction words per task
     uint32_t max_text;              // pairs with a longer text are skipped (host aligns them one by one)
@@ -315,7 +316,7 @@ struct BatchTraceArgs {
     char *out_text;  char *out_pattern;
 };
 
-__global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceArgs A)
+__global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceArgs A)
 {
     // alphabet in shared memory: per-lane indices differ, and a divergent index into the constant bank
     // (kernel parameters) would serialise.  The score matrix is read through L1 (__ldg): the block keeps
@@ -369,11 +370,13 @@ __global__ void __launch_bounds__(128) batch_traceback_kernel(const BatchTraceAr
     // (lane, row-in-lane) of DP row i, kept incrementally: no integer division in the walk
     int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
     const int cbShift = cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3;
+    const bool quadLayout = A.table.packed[cls] == 2;
+    const int PQ = cR / 2 <= 2 ? 2 : cR / 2 <= 4 ? 4 : 8;               // pq_for(R)
     auto fetch = [&](int jj) -> int {
         const int k = (jj - 1) + ll;
-        const int kb = k >> cbShift, kk = k & (cCB - 1);
+        const int kb = quadLayout ? k >> 2 : k >> cbShift, kk = quadLayout ? k & 3 : k & (cCB - 1);
         const int cell = kk * cR + r;
-        const size_t addr = (size_t)(kb * NW + (cell >> cellShift)) * 32 + ll;
+        const size_t addr = quadLayout ? (size_t)(kb * 32 + ll) * PQ + (cell >> 3) : (size_t)(kb * NW + (cell >> cellShift)) * 32 + ll;
         if (addr != cachedAddr) { cachedAddr = addr; cachedWord = dbase[addr]; }
         return (cachedWord >> (2 * (cell & ((1 << cellShift) - 1)) + halfBit)) & 3;
     };

@@ -39,6 +39,13 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t saddr)
     return v;
 }
 
+// Direction words of the straight-line kernels ("quad layout", BatchClassTable.packed == 2): the tags of one lane
+// for FOUR columns (4*R cells x 2 pairs = R/2 words) are contiguous and padded to PQ = 2/4/8 words, a quad of a
+// warp is 32*PQ words:   word(task, q, lane, w) at task*stride + (q*32 + lane)*PQ + w,  cell = (k&3)*R + r.
+// A path that crosses a lane's rows then reads one or two 32-byte sectors per quad instead of a new 128-byte
+// line on almost every step (the warp-step-major layout), which is what bounds the batch traceback.
+__host__ __device__ constexpr int pq_for(int R) { return R / 2 <= 2 ? 2 : R / 2 <= 4 ? 4 : 8; }
+
 template <int R>
 struct Quad16 {
     uint32_t c[R];       // the lane's R cells in the column before the quad (packed A|B)
@@ -116,8 +123,8 @@ template <int R, bool LOCAL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
-    constexpr int CB = cb16_for(R);
-    constexpr int NW = R * CB / 8;          // words per store block (each word: 8 cells x 2 pairs)
+    constexpr int WQ = R / 2;               // direction words per lane and quad (each word: 8 cells x 2 pairs)
+    constexpr int PQ = pq_for(R);
     constexpr int RPAD = rpad_for(R);
     constexpr int PS = 32 * RPAD;
     constexpr int NPW = (R + 3) / 4;
@@ -208,8 +215,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
         for (int r = 0; r < R; ++r) snap.c[r] = 0u;
         snap.top[0] = snap.top[1] = snap.top[2] = snap.top[3] = 0u; snap.diag = 0u;
 
-        uint32_t *dptr = dirs + (size_t)task * A.task_stride + lane;
-        const int nBlocks = (nSteps + CB - 1) / CB;
+        uint32_t *dptr = dirs + (size_t)task * A.task_stride + lane * PQ;
         uint32_t pTextA = stextA + 4 * word0, pTextB = stextB + 4 * word0;
         uint32_t wA0 = lds_u32(pTextA), wB0 = lds_u32(pTextB);
 
@@ -224,9 +230,9 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
             for (int r = 0; r < R; ++r) cur.c[r] = c[r];
             cur.diag = prevTop;
             uint32_t cm[4];
-            uint32_t acc[NW];
+            uint32_t acc[PQ];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) acc[w] = 0;
+            for (int w = 0; w < PQ; ++w) acc[w] = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
 #pragma unroll
                 for (int w = 0; w < NPW; ++w) { pa[w] = lds_u32(aA + 4 * w); pb[w] = lds_u32(aB + 4 * w); }
                 uint32_t bmax[nblk_for(R)];
-                sweep_column16<R, LOCAL, NW>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * (k % CB), bmax);
+                sweep_column16<R, LOCAL, PQ>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * k, bmax);
                 cur.top[k] = top;
                 prevTop = top;
                 bottom = c[R - 1];
@@ -249,17 +255,15 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
                     for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
                     cm[k] = m;
                 }
-                if ((k + 1) % CB == 0) {
-                    const int kb = (4 * q + k) / CB;
-                    if (CB == 4 || kb < nBlocks) {
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) dptr[(size_t)w * 32] = acc[w];
-                    }
-                    dptr += NW * 32;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) acc[w] = 0;
-                }
             }
+            // the quad's tags: one or two 128-bit stores per lane
+            if (PQ == 2) *reinterpret_cast<uint2 *>(dptr) = make_uint2(acc[0], acc[1]);
+            else {
+#pragma unroll
+                for (int w = 0; w < PQ; w += 4)
+                    *reinterpret_cast<uint4 *>(dptr + w) = make_uint4(acc[w], acc[w + 1 < PQ ? w + 1 : 0], acc[w + 2 < PQ ? w + 2 : 0], acc[w + 3 < PQ ? w + 3 : 0]);
+            }
+            dptr += 32 * PQ;
 
             if (!LOCAL) continue;        // global: the end cell is (m, n) and the traceback re-derives the score
             // ---- arg-max bookkeeping, once per quad

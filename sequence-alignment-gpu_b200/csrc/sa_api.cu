@@ -236,7 +236,14 @@ bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, bool line, 
         std::sort(cfgs.begin(), cfgs.end(), [](const BatchCfg &x, const BatchCfg &y) { return x.R * x.L < y.R * y.L; });
     }
     if (cfgs.empty() || (uint32_t)(cfgs.back().R * cfgs.back().L) < max_m) {
-        if (allow16) cfgs.assign(std::begin(kBatchCfgs16), std::end(kBatchCfgs16));
+        if (allow16) {
+            cfgs.assign(std::begin(kBatchCfgs16), std::end(kBatchCfgs16));
+            if (line && sw16_exists(BatchCfg{9, 32})) {       // the straight-line kernels also come in odd strip heights: finer classes, fuller lanes
+                cfgs.push_back(BatchCfg{9, 32});
+                cfgs.push_back(BatchCfg{11, 32});
+                std::sort(cfgs.begin(), cfgs.end(), [](const BatchCfg &x, const BatchCfg &y) { return x.R * x.L < y.R * y.L; });
+            }
+        }
         else cfgs.assign(std::begin(kBatchCfgs), std::end(kBatchCfgs));
     }
     std::memset(T, 0, sizeof *T);
@@ -245,7 +252,7 @@ bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, bool line, 
         const int k = T->n_classes++;
         T->R[k] = c.R; T->L[k] = c.L; T->max_rows[k] = (uint32_t)(c.R * c.L);
         // 2: straight-line kernel with the quad direction layout, 1: batch_fill16_kernel, 0: s32 kernel
-        T->packed[k] = !(allow16 && cfg16_exists(c.R, c.L)) ? 0 : (line && sw16_exists(c)) ? 2 : 1;
+        T->packed[k] = !allow16 ? 0 : (line && sw16_exists(c)) ? 2 : cfg16_exists(c.R, c.L) ? 1 : 0;
         T->stride[k] = batch_task_stride(c, max_n, T->packed[k]);
         if ((uint32_t)(c.R * c.L) >= max_m) break;      // larger classes cannot occur
     }
@@ -329,7 +336,7 @@ int occupancy_batch16(const BatchCfg &cfg, bool local, size_t smem)
 }
 
 // straight-line packed SW kernel (sa_batch16_sw.cuh): L = 32 classes only
-#define SA_SW16_R_LIST(X) X(4) X(6) X(8) X(10) X(12)
+#define SA_SW16_R_LIST(X) X(4) X(6) X(8) X(9) X(10) X(11) X(12)
 bool sw16_exists(const BatchCfg &cfg)
 {
     static const bool off = [] { const char *e = std::getenv("SA_BATCH_SW16"); return e && e[0] == '0'; }();

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
     int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
     const int cbShift = cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3;
     const bool quadLayout = A.table.packed[cls] == 2;
-    const int PQ = ((cR + 1) / 2 + 1) & ~1;                             // pq_for(R)
+    const int PQ = (cR + 1) / 2 <= 2 ? 2 : (cR + 1) / 2 <= 4 ? 4 : 8;   // pq_for(R)
     auto fetch = [&](int jj) -> int {
         const int k = (jj - 1) + ll;
         const int kb = quadLayout ? k >> 2 : k >> cbShift, kk = quadLayout ? k & 3 : k & (cCB - 1);

@@ -40,11 +40,11 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t saddr)
 }
 
 // Direction words of the straight-line kernels ("quad layout", BatchClassTable.packed == 2): the tags of one lane
-// for FOUR columns (4*R cells x 2 pairs = ceil(R/2) words) are contiguous and padded to an even PQ words, a quad of a
+// for FOUR columns (4*R cells x 2 pairs = ceil(R/2) words) are contiguous and padded to PQ = 2/4/8 words, a quad of a
 // warp is 32*PQ words:   word(task, q, lane, w) at task*stride + (q*32 + lane)*PQ + w,  cell = (k&3)*R + r.
 // A path that crosses a lane's rows then reads one or two 32-byte sectors per quad instead of a new 128-byte
 // line on almost every step (the warp-step-major layout), which is what bounds the batch traceback.
-__host__ __device__ constexpr int pq_for(int R) { return ((R + 1) / 2 + 1) & ~1; }
+__host__ __device__ constexpr int pq_for(int R) { return (R + 1) / 2 <= 2 ? 2 : (R + 1) / 2 <= 4 ? 4 : 8; }
 
 template <int R>
 struct Quad16 {
@@ -122,7 +122,7 @@ __host__ __device__ constexpr Sw16Layout sw16_layout(int R, int alpha, uint32_t 
 template <int R, bool LOCAL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArgs A)
 {
-    static_assert(R >= 2 && R <= 16, "strip height");
+    static_assert(R >= 2 && R <= 16, "4*R cells of a quad must fit PQ <= 8 words");
     constexpr int PQ = pq_for(R);
     constexpr int RPAD = rpad_for(R);
     constexpr int PS = 32 * RPAD;
@@ -255,9 +255,13 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
                     cm[k] = m;
                 }
             }
-            // the quad's tags: PQ/2 64-bit stores per lane (the lane's 8*PQ bytes are contiguous)
+            // the quad's tags: one or two 128-bit stores per lane
+            if (PQ == 2) *reinterpret_cast<uint2 *>(dptr) = make_uint2(acc[0], acc[1]);
+            else {
 #pragma unroll
-            for (int w = 0; w < PQ; w += 2) *reinterpret_cast<uint2 *>(dptr + w) = make_uint2(acc[w], acc[w + 1]);
+                for (int w = 0; w < PQ; w += 4)
+                    *reinterpret_cast<uint4 *>(dptr + w) = make_uint4(acc[w], acc[w + 1 < PQ ? w + 1 : 0], acc[w + 2 < PQ ? w + 2 : 0], acc[w + 3 < PQ ? w + 3 : 0]);
+            }
             dptr += 32 * PQ;
 
             if (!LOCAL) continue;        // global: the end cell is (m, n) and the traceback re-derives the score

@@ -48,7 +48,7 @@ def dummy_request(rows, cols, rng):
     return rng.integers(0, 22, cols - 1, dtype=np.uint8), rng.integers(0, 22, rows - 1, dtype=np.uint8)
 
 
-def throughput(al, mode, sizes, cpu, rng):
+def throughput(al, mode, sizes, cpu, rng, refgpu=None):
     name = "Global" if mode == 0 else "Local"
     print(f"\n{name} alignment benchmark:")
     mat = blosum50()
@@ -77,6 +77,12 @@ def throughput(al, mode, sizes, cpu, rng):
         print(f"GPU = {gpu_us / 1000:.3f} ms\nMCUPS: {int(rows * cols / gpu_us)}\n")
         if cpu_us:
             print(f"GPU Speedup = {cpu_us / gpu_us:.1f}")
+        if refgpu is not None and rows * cols <= (1 << 32):
+            # the reference's own kernels on this GPU, timed by its own BENCHMARK switch (fill + D2H of 1 B/cell)
+            rbest = min(refgpu.fill_micros(mode, 23, mat, 5, t, p) for _ in range(3))
+            rbest = max(1, rbest)
+            print(f"reference GPU (alignSequenceGPU.cu, same device) = {rbest / 1000:.3f} ms\nMCUPS: {int(rows * cols / rbest)}")
+            print(f"speed-up over the reference GPU path = {rbest / gpu_us:.1f}\n")
 
 
 def latency(al, mode, sizes, rng):
@@ -123,6 +129,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency", "batch", "maxlength", "all"])
     ap.add_argument("--cpu", action="store_true", help="also time the reference CPU fill (oracle/_ref)")
+    ap.add_argument("--ref-gpu", action="store_true",
+                    help="also time the reference's own GPU path on this device (oracle/_ref/libsa_refgpu_bench.so)")
     ap.add_argument("--max-size", type=int, default=65536)
     args = ap.parse_args()
     sa = load_package()
@@ -130,9 +138,13 @@ def main():
     al = sa.Aligner(0)
     rng = np.random.default_rng(0)
     print("Benchmark on GPU: B200 (libsa_b200, %s)" % sa.lib().sa_version().decode())
+    refgpu = None
+    if args.ref_gpu:
+        from oracle.oracle_py import ReferenceGpu
+        refgpu = ReferenceGpu(bench=True)
     if args.mode in ("throughput", "all"):
-        throughput(al, 0, [s for s in NW_SIZES if s[0] <= args.max_size], args.cpu, rng)
-        throughput(al, 1, [s for s in SW_SIZES if s[0] <= args.max_size], args.cpu, rng)
+        throughput(al, 0, [s for s in NW_SIZES if s[0] <= args.max_size], args.cpu, rng, refgpu)
+        throughput(al, 1, [s for s in SW_SIZES if s[0] <= args.max_size], args.cpu, rng, refgpu)
     if args.mode in ("latency", "all"):
         latency(al, 0, [s for s in LAT_NW_SIZES if s[0] <= args.max_size], rng)
         latency(al, 1, [s for s in SW_SIZES if s[0] <= args.max_size], rng)

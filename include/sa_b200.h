@@ -169,6 +169,21 @@ int sa_strip_traceback(sa_context *ctx, uint64_t start_row,
                        char *d_aligned_text, char *d_aligned_pattern, uint64_t cap,
                        uint64_t *d_result4, void *stream);
 
+/* ---- front end: files -> Request buffers (host code; replaces utilities.cpp:31-129 for callers of this library).
+ * sa_validate_and_transform restates validateAndTransform (utilities.cpp:31-63) in place: FASTA header lines are
+ * skipped, lower case is folded, everything outside A-Z is dropped, the residues become alphabet indices; returns
+ * their number, or 0 when a letter is not in the alphabet (*bad_letter, may be NULL).
+ * sa_read_sequence_file = readSequenceFile (:65-104): *out is malloc'ed (sa_free).  sa_parse_score_matrix_file =
+ * parseScoreMatrixFile (:106-129) but a missing file is an error instead of a silent success.
+ * sa_read_fasta_batch (new): every record of a multi-FASTA file becomes one sequence of a CSR batch. */
+int64_t sa_validate_and_transform(char *buf, uint64_t len, const char *alphabet, int alphabet_size, char *bad_letter);
+int sa_read_sequence_file(const char *path, const char *alphabet, int alphabet_size, uint8_t **out, uint64_t *n,
+                          char *bad_letter);
+int sa_parse_score_matrix_file(const char *path, int alphabet_size, int32_t *matrix);
+int sa_read_fasta_batch(const char *path, const char *alphabet, int alphabet_size, uint8_t **residues,
+                        int64_t **offsets, uint64_t *n_records, char *bad_letter);
+void sa_free(void *p);
+
 /* ---- batch of independent pairs (new surface; the reference's "batch" is a
  * loop of single calls, tests/benchmarks.cu:318-322) --------------------------
  * CSR layout: pair p's text is text[text_off[p] .. text_off[p+1]) and likewise

@@ -230,3 +230,43 @@ class Reference:
         self.lib.ref_pretty_print(aln.aligned_text, aln.aligned_pattern, aln.aln_len,
                                   aln.start_text, aln.start_pattern, aln.score, buf, need)
         return buf.raw[:need]
+
+
+class ReferenceGpu:
+    """The unmodified reference's GPU path (alignSequenceGPU.cu) as a secondary baseline on the same device.
+    bench=True loads the -DBENCHMARK build: fill_micros() returns what tests/benchmarks.cu:171-175 measures
+    (kernels + device-to-host copy of the 1 byte/cell direction matrix, no allocation / H2D / traceback)."""
+
+    def __init__(self, bench: bool = True):
+        path = os.path.join(HERE, "_ref", "libsa_refgpu_bench.so" if bench else "libsa_ref_O3.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.bench = bench
+        self.lib = C.CDLL(path)
+        self.lib.ref_align_gpu.restype = C.c_uint64
+        self.lib.ref_align_gpu.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
+                                           C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+
+    def _call(self, mode, alpha, matrix, gap, text, pattern, outT=None, outP=None):
+        text, pattern = _u8(text), _u8(pattern)
+        full = np.zeros(23 * 23, np.int32)
+        full[:alpha * alpha] = _i32(matrix).ravel()[:alpha * alpha]
+        score, ln, st, sp = C.c_int(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        r = self.lib.ref_align_gpu(mode, alpha, full.ctypes.data, gap, text.ctypes.data, len(text), pattern.ctypes.data,
+                                   len(pattern), C.byref(score), C.byref(ln), C.byref(st), C.byref(sp),
+                                   outT.ctypes.data if outT is not None else None, outP.ctypes.data if outP is not None else None)
+        return r, score.value, ln.value, st.value, sp.value
+
+    def fill_micros(self, mode, alpha, matrix, gap, text, pattern) -> int:
+        assert self.bench
+        return int(self._call(mode, alpha, matrix, gap, text, pattern)[0])
+
+    def align(self, mode, alpha, matrix, gap, text, pattern) -> Alignment:
+        assert not self.bench
+        n = len(text)
+        outT = np.empty(max(1, 2 * n), np.uint8); outP = np.empty(max(1, 2 * n), np.uint8)
+        r, score, ln, st, sp = self._call(mode, alpha, matrix, gap, text, pattern, outT, outP)
+        if r:
+            raise RuntimeError(f"reference alignSequenceGPU failed ({r})")
+        return Alignment(score, ln, st, sp, outT[:ln].tobytes(), outP[:ln].tobytes())

@@ -164,4 +164,32 @@ uint64_t ref_pretty_print(const char *alnT, const char *alnP, uint64_t len, uint
     return s.size();
 }
 
+// The reference's own GPU path, SequenceAlignment::alignSequenceGPU (alignSequenceGPU.cu:463), unmodified: the
+// secondary baseline "reference kernels on the same B200" of benchmarks.py.  Built normally it
+// returns 0 and fills the response (CPU traceback included); built with -DBENCHMARK (libsa_refgpu_bench.so) it
+// returns the microseconds of fill + device-to-host copy like tests/benchmarks.cu uses it (:613-626).
+uint64_t ref_align_gpu(int mode, int alphabetSize, const int *matrix, int gap,
+                       const char *text, uint64_t n, const char *pattern, uint64_t m,
+                       int *score, uint64_t *alnLen, uint64_t *startText, uint64_t *startPattern,
+                       char *outT, char *outP)
+{
+    SequenceAlignment::Request rq;
+    SequenceAlignment::Response rs;
+    fillRequest(rq, mode, alphabetSize, matrix, gap, text, n, pattern, m);
+    rq.deviceType = SequenceAlignment::programArgs::GPU;
+    const uint64_t r = SequenceAlignment::alignSequenceGPU(rq, &rs);
+#ifdef BENCHMARK
+    return r;
+#else
+    if (r) return r;
+    if (score) *score = rs.score;
+    if (alnLen) *alnLen = rs.numAlignmentBytes;
+    if (startText) *startText = rs.startInAlignedText;
+    if (startPattern) *startPattern = rs.startInAlignedPattern;
+    if (outT) std::memcpy(outT, rs.alignedTextBytes, rs.numAlignmentBytes);
+    if (outP) std::memcpy(outP, rs.alignedPatternBytes, rs.numAlignmentBytes);
+    return 0;
+#endif
+}
+
 } // extern "C"

@@ -132,6 +132,13 @@ def lib() -> C.CDLL:
         L.sa_strip_fill_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
         L.sa_strip_traceback.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.sa_validate_and_transform.restype = C.c_int64
+        L.sa_validate_and_transform.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_char_p]
+        L.sa_read_sequence_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_char_p]
+        L.sa_parse_score_matrix_file.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.sa_read_fasta_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_uint64), C.c_char_p]
+        L.sa_free.argtypes = [C.c_void_p]
         L.sa_partition_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -363,3 +370,59 @@ def alignSequenceGPU(request: Request, response: Response) -> int:
     response.startInAlignedPattern = a.start_pattern
     response.score = a.score
     return 0
+
+
+# ---- front end (utilities.cpp:31-129), through the C ABI -------------------------------------------------------
+def validateAndTransform(data: bytes, alphabet: bytes, alphabetSize: int) -> np.ndarray:
+    """validateAndTransform (utilities.cpp:31-63): FASTA headers skipped, case folded, non-letters dropped, residues
+    -> alphabet indices.  Like the reference, a letter outside the alphabet yields an EMPTY result (it returns 0)
+    after naming the letter on stderr."""
+    buf = C.create_string_buffer(bytes(data), len(data))
+    bad = C.create_string_buffer(1)
+    k = lib().sa_validate_and_transform(buf, len(data), alphabet, alphabetSize, bad)
+    if k == 0 and bad.raw != b"\x00":
+        sys.stderr.write(f"'{bad.raw.decode('latin1')}' letter not in alphabet.\n")
+    return np.frombuffer(buf.raw[:k], np.uint8).copy()
+
+
+def readSequenceFile(fname: str, request: Request) -> int:
+    """readSequenceFile (utilities.cpp:65-104): the first call fills the text, the second the pattern; returns 0,
+    or -1 when the file does not exist."""
+    if not os.path.isfile(fname):
+        sys.stderr.write(f"{fname} file does not exist\n")
+        return -1
+    seq = validateAndTransform(open(fname, "rb").read(), request.alphabet, request.alphabetSize)
+    if request.textNumBytes == 0 and len(seq) > 0:
+        request.textBytes, request.textNumBytes = seq, len(seq)
+    elif request.patternNumBytes == 0 and len(seq) > 0:
+        request.patternBytes, request.patternNumBytes = seq, len(seq)
+    return 0
+
+
+def parseScoreMatrixFile(fname: str, alphabetSize: int, buffer: np.ndarray) -> int:
+    """parseScoreMatrixFile (utilities.cpp:106-129) including its return values: -1 for a malformed file, and 0 --
+    with a message on stderr and the buffer untouched -- for a MISSING one."""
+    if not os.path.isfile(fname):
+        sys.stderr.write(f"{fname} file does not exist\n")
+        return 0
+    tmp = np.zeros(alphabetSize * alphabetSize, np.int32)
+    if lib().sa_parse_score_matrix_file(fname.encode(), alphabetSize, tmp.ctypes.data) != 0:
+        return -1
+    buffer[:alphabetSize * alphabetSize] = tmp
+    return 0
+
+
+def read_fasta_batch(fname: str, alphabet: bytes, alphabetSize: int):
+    """Multi-record FASTA -> (residues uint8, offsets int64) in the CSR form align_batch takes (new surface)."""
+    res, off, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    bad = C.create_string_buffer(1)
+    rc = lib().sa_read_fasta_batch(fname.encode(), alphabet, alphabetSize, C.byref(res), C.byref(off), C.byref(n), bad)
+    if rc != 0:
+        raise SaError(rc, f"cannot read {fname}" + (f": letter '{bad.raw.decode('latin1')}' not in alphabet" if bad.raw != b"\x00" else ""))
+    try:
+        offsets = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), shape=(n.value + 1,)).copy()
+        total = int(offsets[-1])
+        residues = (np.ctypeslib.as_array(C.cast(res, C.POINTER(C.c_uint8)), shape=(max(total, 1),))[:total]).copy()
+    finally:
+        lib().sa_free(res); lib().sa_free(off)
+    return residues, offsets

@@ -326,3 +326,19 @@ def test_full_size_c4_batch_properties(sa, aligner, oracle):
     k = 5000   # strings of the first pairs byte for byte (the arenas' unused slack is not compared)
     for i in range(k):
         assert sa.unpack_batch(out, i).key() == sa.unpack_batch(out32, i).key()
+
+
+def test_reference_gpu_path_agrees(aligner):
+    """Cross-check against the reference's OWN GPU path (alignSequenceGPU.cu, unmodified, oracle/_ref): the drop-in
+    must return what it returns.  Skipped when the reference build did not travel."""
+    from oracle.oracle_py import ReferenceGpu
+    try:
+        ref = ReferenceGpu(bench=False)
+    except (FileNotFoundError, OSError, AttributeError) as e:
+        pytest.skip(f"reference GPU build not available: {e}")
+    rng = np.random.default_rng(77)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b50 = helpers.matrices()["protein/blosum50.txt"]
+    for mode, alpha, mat, n in ((0, 4, blast, 700), (1, 4, blast, 900), (0, 23, b50, 1200), (1, 23, b50, 2500)):
+        t, p = helpers.random_case(rng, alpha, n)
+        assert_same(aligner.align(mode, alpha, mat, 5, t, p), ref.align(mode, alpha, mat, 5, t, p), ("reference GPU", mode, alpha, n))

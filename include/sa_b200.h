@@ -184,6 +184,12 @@ int sa_read_fasta_batch(const char *path, const char *alphabet, int alphabet_siz
                         int64_t **offsets, uint64_t *n_records, char *bad_letter);
 void sa_free(void *p);
 
+/* The report of prettyAlignmentPrint (utilities.cpp:253-315), byte for byte: returns the size of the full report and
+ * writes at most cap bytes of it into out; *identity / *gaps (may be NULL) receive the two counts. */
+uint64_t sa_pretty_print(const char *aligned_text, const char *aligned_pattern, uint64_t len, uint64_t start_text,
+                         uint64_t start_pattern, int32_t score, char *out, uint64_t cap, uint64_t *identity,
+                         uint64_t *gaps);
+
 /* ---- batch of independent pairs (new surface; the reference's "batch" is a
  * loop of single calls, tests/benchmarks.cu:318-322) --------------------------
  * CSR layout: pair p's text is text[text_off[p] .. text_off[p+1]) and likewise

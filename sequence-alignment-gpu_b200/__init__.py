@@ -139,6 +139,9 @@ def lib() -> C.CDLL:
         L.sa_read_fasta_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_uint64), C.c_char_p]
         L.sa_free.argtypes = [C.c_void_p]
+        L.sa_pretty_print.restype = C.c_uint64
+        L.sa_pretty_print.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p,
+                                      C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.sa_partition_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -426,3 +429,21 @@ def read_fasta_batch(fname: str, alphabet: bytes, alphabetSize: int):
     finally:
         lib().sa_free(res); lib().sa_free(off)
     return residues, offsets
+
+
+def prettyAlignmentPrint(response: Response) -> bytes:
+    """prettyAlignmentPrint (utilities.cpp:253-315): the report the reference's driver prints, byte for byte."""
+    L = lib()
+    args = (response.alignedTextBytes, response.alignedPatternBytes, response.numAlignmentBytes,
+            response.startInAlignedText, response.startInAlignedPattern, response.score)
+    need = L.sa_pretty_print(*args, None, 0, None, None)
+    buf = C.create_string_buffer(int(need) + 1)
+    L.sa_pretty_print(*args, buf, need, None, None)
+    return buf.raw[:need]
+
+
+def alignment_stats(aligned_text: bytes, aligned_pattern: bytes):
+    """(identical columns, gap columns) as prettyAlignmentPrint counts them."""
+    ident, gaps = C.c_uint64(), C.c_uint64()
+    lib().sa_pretty_print(aligned_text, aligned_pattern, len(aligned_text), 0, 0, 0, None, 0, C.byref(ident), C.byref(gaps))
+    return ident.value, gaps.value

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 namespace {
@@ -160,6 +161,55 @@ int sa_read_fasta_batch(const char *path, const char *alphabet, int alphabet_siz
     std::memcpy(o, off.data(), off.size() * sizeof(int64_t));
     *residues = r; *offsets = o; *n_records = recs;
     return SA_OK;
+}
+
+// ---- the step after the path: prettyAlignmentPrint (utilities.cpp:253-315), restated ---------------------------
+// Writes the reference's report -- blocks of 50 columns with 1-based positions and a match line ('|' identical,
+// ' ' gap, '.' mismatch), then "# Length / # Identity / # Gaps / # Score" -- into out (capacity cap) and returns the
+// number of bytes the full report needs (call with cap = 0 to size the buffer).  identity / gaps (may be NULL)
+// receive the two counts.  An empty alignment prints nothing, like the reference.
+uint64_t sa_pretty_print(const char *aligned_text, const char *aligned_pattern, uint64_t len, uint64_t start_text,
+                         uint64_t start_pattern, int32_t score, char *out, uint64_t cap, uint64_t *identity,
+                         uint64_t *gaps)
+{
+    if (identity) *identity = 0;
+    if (gaps) *gaps = 0;
+    if (len == 0 || !aligned_text || !aligned_pattern) return 0;
+    std::string s;
+    s.reserve((size_t)len * 4 + 256);
+    const unsigned CHARS_PER_LINE = 50;
+    int width = 0;
+    int maxI = (int)(len + (start_text > start_pattern ? start_text : start_pattern));      // int, like the reference
+    do { maxI /= 10; ++width; } while (maxI != 0);
+    auto padded = [&](const std::string &v) { if ((int)v.size() < width) s.append((size_t)width - v.size(), ' '); s += v; };
+    uint64_t nId = 0, nGap = 0;
+    for (uint64_t i = 0; i < len; i += CHARS_PER_LINE) {
+        const uint64_t end = (i + CHARS_PER_LINE < len) ? i + CHARS_PER_LINE : len;
+        padded(std::to_string(i + 1 + start_text)); s += ' ';
+        s.append(aligned_text + i, (size_t)(end - i));
+        s += "   "; s += std::to_string(end + start_pattern); s += " \n";
+        padded(" "); s += ' ';
+        for (uint64_t j = i; j < end; ++j) {
+            if (aligned_text[j] == aligned_pattern[j]) { s += '|'; ++nId; }
+            else if (aligned_text[j] == '-' || aligned_pattern[j] == '-') { s += ' '; ++nGap; }
+            else s += '.';
+        }
+        s += '\n';
+        padded(std::to_string(i + 1)); s += ' ';
+        s.append(aligned_pattern + i, (size_t)(end - i));
+        s += "   "; s += std::to_string(end); s += "\n\n";
+    }
+    char num[64];
+    s += "# Length: \t" + std::to_string(len) + "\n";
+    std::snprintf(num, sizeof num, "%.3g", (double)nId / ((double)len * 1.0) * 100);
+    s += "# Identity: \t" + std::to_string(nId) + "/" + std::to_string(len) + " (" + num + "%)\n";
+    std::snprintf(num, sizeof num, "%.3g", (double)nGap / ((double)len * 1.0) * 100);
+    s += "# Gaps: \t" + std::to_string(nGap) + "/" + std::to_string(len) + " (" + num + "%)\n";
+    s += "# Score: \t" + std::to_string(score) + "\n";
+    if (identity) *identity = nId;
+    if (gaps) *gaps = nGap;
+    if (out && cap) std::memcpy(out, s.data(), s.size() < cap ? s.size() : (size_t)cap);
+    return s.size();
 }
 
 } // extern "C"

@@ -92,3 +92,23 @@ def test_read_fasta_batch(reference, tmp_path):
     with pytest.raises(sa.SaError):
         h = tmp_path / "bad.fasta"; h.write_bytes(b">x\nACGTN\n")
         sa.read_fasta_batch(str(h), DNA, 4)
+
+
+def test_pretty_print_matches_reference(reference, oracle):
+    """prettyAlignmentPrint byte for byte, on golden alignments of all kinds (short, multi-line, wide position columns,
+    local alignments with non-zero starts) and the empty alignment."""
+    sa = load_package()
+    from oracle.oracle_py import Alignment
+    gs = helpers.goldens()
+    small = [g for g in gs if g["n"] * g["m"] <= 4_000_000]
+    picked = [g for g in small if g["ref"]["aln_len"] > 0][:: max(1, len(small) // 40)] + [g for g in small if g["ref"]["aln_len"] == 0][:2]
+    assert len(picked) > 20
+    for g in picked:
+        t, p, mat = helpers.golden_inputs(g)
+        a = oracle.align(g["mode"], g["alpha"], mat, g["gap"], t, p)
+        rs = sa.Response(alignedTextBytes=a.aligned_text, alignedPatternBytes=a.aligned_pattern, numAlignmentBytes=a.aln_len,
+                         startInAlignedText=a.start_text, startInAlignedPattern=a.start_pattern, score=a.score)
+        want = reference.pretty_print(Alignment(a.score, a.aln_len, a.start_text, a.start_pattern, a.aligned_text, a.aligned_pattern))
+        assert sa.prettyAlignmentPrint(rs) == want, g.get("name")
+    ident, gaps = sa.alignment_stats(b"AC-GT", b"ACTG-")
+    assert (ident, gaps) == (3, 2)

@@ -318,137 +318,139 @@ struct BatchTraceArgs {
 
 __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceArgs A)
 {
-    // alphabet in shared memory: per-lane indices differ, and a divergent index into the constant bank
-    // (kernel parameters) would serialise.  The score matrix is read through L1 (__ldg): the block keeps
-    // its shared-memory footprint minimal so that it fits next to the fill blocks of the next chunk.
-    __shared__ char alphS[MAX_ALPHA + 1];
-    for (int i = threadIdx.x; i <= A.alpha; i += blockDim.x) alphS[i] = A.alphabet[i];
+    // Alphabet (+ gap character at index alpha) and the score matrix as bytes in shared memory: per-lane indices
+    // differ, and a divergent index into the constant bank (kernel parameters) would serialise.  ~1.1 KB per block,
+    // so that the block still fits next to the fill blocks of the next chunk.
+    __shared__ unsigned char alphS[MAX_ALPHA + 1];
+    __shared__ signed char S8[MAX_ALPHA * MAX_ALPHA];
+    for (int i = threadIdx.x; i <= A.alpha; i += blockDim.x) alphS[i] = (unsigned char)A.alphabet[i];
+    for (int i = threadIdx.x; i < A.alpha * A.alpha; i += blockDim.x) S8[i] = (signed char)A.S[i];      // |S| <= 31 (upload_scoring)
     __syncthreads();
+    const int alpha = A.alpha, gap = A.gap;
     // grid-stride over the pairs: a pipelined chunk launches only a few blocks per SM so that the fill blocks of the
     // next chunk fit next to them (a full grid would hold every SM until the traceback drains)
     for (uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x; gpos < A.dyn[A.table.n_classes].first; gpos += gridDim.x * blockDim.x) {
-    int cls = 0;
-    while (gpos >= A.dyn[cls].first + A.dyn[cls].count) ++cls;
-    const int cR = A.table.R[cls], cL = A.table.L[cls];
-    const bool packed = A.table.packed[cls] != 0;
-    // s32 layout: 16 cells per word; s16x2 layout: 8 cells per half-word, the pair's half picked by parity
-    const int cCB = packed ? ((cR % 8 == 0) ? 1 : (cR % 4 == 0) ? 2 : 4) : cb_for(cR);
-    const int cellShift = packed ? 3 : 4;
-    const int G = 32 / cL, NW = (cR * cCB) >> cellShift;
-    const uint32_t pos = gpos - A.dyn[cls].first;
-    const uint32_t pair = A.order[gpos];
-    const uint32_t unit = packed ? pos >> 1 : pos;
-    const int halfBit = packed ? (int)(pos & 1) * 16 : 0;
-    const uint32_t task = unit / G, g = unit % G;
-    const int64_t t0 = A.text_off[pair], p0 = A.pattern_off[pair];
-    const int n = (int)(A.text_off[pair + 1] - t0), m = (int)(A.pattern_off[pair + 1] - p0);
-    const uint8_t *tx = A.text + t0, *pt = A.pattern + p0;
-    const uint32_t *dbase = A.dirs + A.dyn[cls].dir_base + (size_t)task * A.table.stride[cls] + g * cL;
-    const char GAPC = alphS[A.alpha];
-    const uint64_t slotEnd = (uint64_t)(t0 + p0) + (uint64_t)(n + m);
+        int cls = 0;
+        while (gpos >= A.dyn[cls].first + A.dyn[cls].count) ++cls;
+        const int cR = A.table.R[cls], cL = A.table.L[cls];
+        const int layout = A.table.packed[cls];                  // 0: s32, 1: s16x2 warp-step-major, 2: s16x2 quad layout
+        const bool packed = layout != 0;
+        const int cCB = layout == 1 ? ((cR % 8 == 0) ? 1 : (cR % 4 == 0) ? 2 : 4) : cb_for(cR);
+        const int G = 32 / cL;
+        const uint32_t pos = gpos - A.dyn[cls].first;
+        const uint32_t pair = A.order[gpos];
+        const uint32_t unit = packed ? pos >> 1 : pos;
+        const int halfBit = packed ? (int)(pos & 1) * 16 : 0;
+        const uint32_t task = unit / G, g = unit % G;
+        const int64_t t0 = A.text_off[pair], p0 = A.pattern_off[pair];
+        const int n = (int)(A.text_off[pair + 1] - t0), m = (int)(A.pattern_off[pair + 1] - p0);
+        const uint8_t *tx = A.text + t0, *pt = A.pattern + p0;
+        const uint32_t *dbase = A.dirs + A.dyn[cls].dir_base + (size_t)task * A.table.stride[cls] + g * cL;
+        const uint64_t slotEnd = (uint64_t)(t0 + p0) + (uint64_t)(n + m);
 
-    int i = (int)A.end_i[pair], j = (int)A.end_j[pair];
-    int H = A.local ? A.score[pair] : 0;           // global: accumulated along the path (the fill does not report it)
-    uint64_t len = 0;
-    size_t cachedAddr = ~(size_t)0; uint32_t cachedWord = 0;
+        // One formula for the three direction layouts: step k = column-1 + lane, block kb = k >> kbShift, step in
+        // block kk, cell = kk*R + r; the word of a cell is kb*KBS + lane*LS + (cell >> cs)*CS (32-bit: a task has
+        // fewer than 2^32 words).
+        const int cs = packed ? 3 : 4;
+        const int kbShift = layout == 2 ? 2 : (cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3);
+        const int kkMask = (1 << kbShift) - 1;
+        const int PQ = (cR + 1) / 2 <= 2 ? 2 : (cR + 1) / 2 <= 4 ? 4 : 8;                 // pq_for(R)
+        const uint32_t KBS = layout == 2 ? 32u * PQ : (uint32_t)((cR * cCB) >> cs) * 32u;
+        const uint32_t LS = layout == 2 ? (uint32_t)PQ : 1u, CS = layout == 2 ? 1u : 32u;
+        const int cmask = (1 << cs) - 1;
 
-    // The walk is bound by L1TEX sector traffic (every lane touches its own pair), so everything is
-    // moved in aligned 32-bit words: residues are read a word at a time and kept in registers, output
-    // characters are packed and stored a word at a time.
-    struct WordReader {
-        const uint32_t *base; int off; int curw; uint32_t w;
-        __device__ WordReader(const uint8_t *p) : base(reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3)),
-                                                   off((int)(reinterpret_cast<uintptr_t>(p) & 3)), curw(-1), w(0) {}
-        __device__ __forceinline__ int get(int q) {
-            const int a = q + off, wi = a >> 2;
-            if (wi != curw) { curw = wi; w = base[wi]; }
-            return (int)((w >> ((a & 3) * 8)) & 0xffu);
-        }
-    };
-    WordReader rdT(tx), rdP(pt);
+        int i = (int)A.end_i[pair], j = (int)A.end_j[pair];
+        int H = A.local ? A.score[pair] : 0;       // global: accumulated along the path (the fill does not report it)
+        uint32_t len = 0;
+        uint32_t cachedIdx = ~0u, cachedWord = 0;
+        // (lane, row-in-lane) of DP row i, kept incrementally: no integer division in the walk
+        int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
+        auto fetch = [&](const int jj) -> int {
+            const int k = (jj - 1) + ll;
+            const int cell = (k & kkMask) * cR + r;
+            const uint32_t idx = (uint32_t)(k >> kbShift) * KBS + (uint32_t)ll * LS + (uint32_t)(cell >> cs) * CS;
+            if (idx != cachedIdx) { cachedIdx = idx; cachedWord = dbase[idx]; }
+            return (cachedWord >> (2 * (cell & cmask) + halfBit)) & 3;
+        };
+        auto row_up = [&]() { --i; if (r == 0) { r = cR - 1; --ll; } else --r; };
 
-    // (lane, row-in-lane) of DP row i, kept incrementally: no integer division in the walk
-    int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
-    const int cbShift = cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3;
-    const bool quadLayout = A.table.packed[cls] == 2;
-    const int PQ = (cR + 1) / 2 <= 2 ? 2 : (cR + 1) / 2 <= 4 ? 4 : 8;   // pq_for(R)
-    auto fetch = [&](int jj) -> int {
-        const int k = (jj - 1) + ll;
-        const int kb = quadLayout ? k >> 2 : k >> cbShift, kk = quadLayout ? k & 3 : k & (cCB - 1);
-        const int cell = kk * cR + r;
-        const size_t addr = quadLayout ? (size_t)(kb * 32 + ll) * PQ + (cell >> 3) : (size_t)(kb * NW + (cell >> cellShift)) * 32 + ll;
-        if (addr != cachedAddr) { cachedAddr = addr; cachedWord = dbase[addr]; }
-        return (cachedWord >> (2 * (cell & ((1 << cellShift) - 1)) + halfBit)) & 3;
-    };
-    auto row_up = [&]() { --i; if (r == 0) { r = cR - 1; --ll; } else --r; };
+        // Residues are read an aligned word at a time and kept in registers; output characters are packed and
+        // stored an aligned word at a time (every lane walks its own pair: sector traffic is what counts).
+        struct WordReader {
+            const uint32_t *base; int off; int curw; uint32_t w;
+            __device__ WordReader(const uint8_t *p) : base(reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3)),
+                                                       off((int)(reinterpret_cast<uintptr_t>(p) & 3)), curw(-1), w(0) {}
+            __device__ __forceinline__ int get(const int q) {
+                const int a = q + off, wi = a >> 2;
+                if (wi != curw) { curw = wi; w = base[wi]; }
+                return (int)((w >> ((a & 3) * 8)) & 0xffu);
+            }
+        };
+        WordReader rdT(tx), rdP(pt);
 
-    // backwards writer: bytes go to decreasing addresses; whole aligned words when possible
-    char *const baseT = A.out_text, *const baseP = A.out_pattern;
-    const bool wordOK = ((reinterpret_cast<uintptr_t>(baseT) ^ reinterpret_cast<uintptr_t>(baseP)) & 3) == 0;
-    uint64_t wp = slotEnd;                       // the next byte goes to wp-1
-    uint32_t accT = 0, accP = 0; int cnt = 0;
-    auto emit = [&](const unsigned cT, const unsigned cP) {
-        --wp;
-        const bool top = (reinterpret_cast<uintptr_t>(baseT + wp) & 3) == 3;
-        if (!wordOK || (cnt == 0 && !top)) { baseT[wp] = (char)cT; baseP[wp] = (char)cP; return; }
-        accT = (accT << 8) | cT;                  // little-endian: the lowest address ends up in bits 7:0
-        accP = (accP << 8) | cP;
-        if (++cnt == 4) {
-            *reinterpret_cast<uint32_t *>(baseT + wp) = accT;
-            *reinterpret_cast<uint32_t *>(baseP + wp) = accP;
-            cnt = 0;
-        }
-    };
-    auto flush = [&]() {
-        for (int q = 0; q < cnt; ++q) {
-            baseT[wp + q] = (char)((accT >> (8 * q)) & 0xffu);
-            baseP[wp + q] = (char)((accP >> (8 * q)) & 0xffu);
-        }
-        cnt = 0;
-    };
+        // backwards writer: the next byte goes to p-1.  Up to three single bytes until the addresses are word
+        // aligned, then whole words (both strings share the alignment, or bytes only)
+        char *pT = A.out_text + slotEnd, *pP = A.out_pattern + slotEnd;
+        const bool wordOK = ((reinterpret_cast<uintptr_t>(pT) ^ reinterpret_cast<uintptr_t>(pP)) & 3) == 0;
+        int head = wordOK ? (int)(reinterpret_cast<uintptr_t>(pT) & 3) : 0x7fffffff;
+        uint32_t accT = 0, accP = 0; int cnt = 0;
+        auto emit = [&](const uint32_t cT, const uint32_t cP) {
+            if (head > 0) { *--pT = (char)cT; *--pP = (char)cP; --head; return; }
+            accT = (accT << 8) | cT;                  // little-endian: the lowest address ends up in bits 7:0
+            accP = (accP << 8) | cP;
+            if (++cnt == 4) {
+                pT -= 4; pP -= 4;
+                *reinterpret_cast<uint32_t *>(pT) = accT;
+                *reinterpret_cast<uint32_t *>(pP) = accP;
+                cnt = 0;
+            }
+        };
 
-    int ti, pi;
-    if (!A.local) {
-        ti = n - 1; pi = m - 1;
-        while (i > 0 || j > 0) {
-            int tag;
-            if (j == 0) tag = TAG_TOP;             // alignSequenceCPU.cpp:78-79
-            else if (i == 0) tag = TAG_LEFT;       // :80-81
-            else tag = fetch(j);
-            const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
-            ++len;
-            const int ct = rdT.get(ti), cp = rdP.get(pi);
-            emit(takeT ? (unsigned)alphS[ct] : (unsigned)GAPC, takeP ? (unsigned)alphS[cp] : (unsigned)GAPC);
-            H += (tag == TAG_DIAG) ? __ldg(A.S + cp * A.alpha + ct) : -A.gap;      // the path's score is H(m, n)
-            ti = max(0, ti - (int)takeT);
-            pi = max(0, pi - (int)takeP);
-            if (takeP) row_up();
-            j -= takeT;
+        int ti, pi;
+        if (!A.local) {
+            ti = n - 1; pi = m - 1;
+            while (i > 0 || j > 0) {
+                int tag;
+                if (j == 0) tag = TAG_TOP;             // alignSequenceCPU.cpp:78-79
+                else if (i == 0) tag = TAG_LEFT;       // :80-81
+                else tag = fetch(j);
+                const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
+                ++len;
+                const int ct = rdT.get(ti), cp = rdP.get(pi);
+                emit(alphS[takeT ? ct : alpha], alphS[takeP ? cp : alpha]);
+                H += (tag == TAG_DIAG) ? (int)S8[cp * alpha + ct] : -gap;      // the path's score is H(m, n)
+                ti = max(0, ti - (int)takeT);
+                pi = max(0, pi - (int)takeP);
+                if (takeP) row_up();
+                j -= takeT;
+            }
+        } else {
+            ti = j - 1; pi = i - 1;                    // :13-14 (-1/-1 when the best score is 0)
+            while (H > 0) {                            // H(i,j) == 0  <=>  reference STOP
+                const int tag = fetch(j);
+                const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
+                ++len;
+                const int ct = rdT.get(ti), cp = rdP.get(pi);      // ti == j-1 and pi == i-1 inside the matrix
+                emit(alphS[takeT ? ct : alpha], alphS[takeP ? cp : alpha]);
+                H += (tag == TAG_DIAG) ? -(int)S8[cp * alpha + ct] : gap;
+                if (takeP) row_up();
+                j -= takeT;
+                if (i == 0 || j == 0) break;           // :45-46, before the index update
+                ti = max(0, ti - (int)takeT);
+                pi = max(0, pi - (int)takeP);
+            }
         }
-    } else {
-        ti = j - 1; pi = i - 1;                    // :13-14 (-1/-1 when the best score is 0)
-        while (H > 0) {                            // H(i,j) == 0  <=>  reference STOP
-            const int tag = fetch(j);
-            const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
-            ++len;
-            const int ct = rdT.get(ti), cp = rdP.get(pi);      // ti == j-1 and pi == i-1 inside the matrix
-            emit(takeT ? (unsigned)alphS[ct] : (unsigned)GAPC, takeP ? (unsigned)alphS[cp] : (unsigned)GAPC);
-            if (tag == TAG_DIAG) H -= __ldg(A.S + cp * A.alpha + ct); else H += A.gap;
-            if (takeP) row_up();
-            j -= takeT;
-            if (i == 0 || j == 0) break;           // :45-46, before the index update
-            ti = max(0, ti - (int)takeT);
-            pi = max(0, pi - (int)takeP);
+        for (int q = cnt - 1; q >= 0; --q) {           // the characters still in the accumulators, oldest first
+            *--pT = (char)((accT >> (8 * q)) & 0xffu);
+            *--pP = (char)((accP >> (8 * q)) & 0xffu);
         }
-    }
-    flush();
-    sa_result res;
-    res.score = A.local ? A.score[pair] : H;
-    res.aln_len = len;
-    res.start_text = (uint64_t)(int64_t)ti;
-    res.start_pattern = (uint64_t)(int64_t)pi;
-    A.results[pair] = res;
-    A.aln_off[pair] = slotEnd - len;
+        sa_result res;
+        res.score = A.local ? A.score[pair] : H;
+        res.aln_len = len;
+        res.start_text = (uint64_t)(int64_t)ti;
+        res.start_pattern = (uint64_t)(int64_t)pi;
+        A.results[pair] = res;
+        A.aln_off[pair] = slotEnd - len;
     }
 }
 

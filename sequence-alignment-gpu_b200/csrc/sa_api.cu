@@ -1093,8 +1093,14 @@ int sa_strip_fill_rows(sa_context *ctx, uint64_t row0, uint64_t rows, const int3
     cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
     SA_TRY(launch_long(S.R, A, false, grid, S.smem, st), SA_ERR_LAUNCH);
-    cudaEventRecord(e1, st); cudaEventRecord(e2, st); cudaEventRecord(e3, st);
     ctx->timing.kernel_launches++;
+    if (A.bottom_row) {     // the last strip left its bottom row in its ring row
+        const unsigned long long *row = A.rowbuf + (size_t)((nStrips - 1) % ring) * S.row_stride;
+        long_bottom_row_kernel<<<(unsigned)((S.n + 255) / 256), 256, 0, st>>>(row, A.bottom_row, (uint32_t)S.n);
+        SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+        ctx->timing.kernel_launches++;
+    }
+    cudaEventRecord(e1, st); cudaEventRecord(e2, st); cudaEventRecord(e3, st);
     ctx->timing_dirty = true;
     return SA_OK;
 }

@@ -55,6 +55,12 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// the same store under a predicate instead of a branch: a divergent `if (lane == 31)` in every step splits the
+// step into basic blocks and keeps the scheduler from interleaving the bookkeeping with the cell chain
+__device__ __forceinline__ void st_volatile_u64_if(const bool pred, unsigned long long *p, unsigned long long v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.volatile.global.u64 [%0], %1;\n\t}" ::"l"(p), "l"(v), "r"((unsigned)pred) : "memory");
+}
 
 constexpr int PB = 8;   // boundary-row prefetch block (columns)
 
@@ -121,6 +127,9 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         int bestv = 0, besti = 0, bestj = 0;
         int gmCached = 0;                               // lane-local copy of *A.gmax (a lower bound)
         const bool hasUp = s > 0, hasDown = s + 1 < A.n_strips;
+        // lane 31 publishes the strip's bottom row for the strip below -- or, for the last strip of a row chunk, for
+        // long_bottom_row_kernel, which copies it out of the ring
+        const bool writesRow = lane == 31 && (hasDown || A.bottom_row != nullptr);
         const unsigned long long *rowIn = A.rowbuf + (size_t)((s + A.ring - 1) % A.ring) * A.row_stride;
         unsigned long long *rowOut = A.rowbuf + (size_t)(s % A.ring) * A.row_stride;
         const unsigned long long wantTag = (unsigned long long)(A.tag_base | s);          // producer s-1 writes (s-1)+1
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         uint32_t acc[NW];
 #pragma unroll
         for (int w = 0; w < NW; ++w) acc[w] = 0;
+        int upN = __shfl_up_sync(0xffffffffu, bottom, 1);
 
         // One wavefront step.  MODE 1 = steady state (every lane has a column, upkeep done by the
         // caller), MODE 2 = ramp-up (same, but lanes whose first column has not arrived yet idle),
@@ -196,16 +206,22 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             const bool nextActive = MODE == 1 || (MODE == 2 ? jn >= 0 : (jn >= 0 && jn < n));
             const int letterN = nextActive ? (int)textWin[jn & 63] : 0;
             topN = topWin[k1 & (2 * PB - 1)];
-            const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
-            if (MODE == 1 || (MODE == 2 ? jt >= 0 : (jt >= 0 && jt < n))) {
+            const int up = upN;                     // exchanged right after the previous step's sweep
+            const bool active = MODE == 1 || (MODE == 2 ? jt >= 0 : (jt >= 0 && jt < n));
+            int bmax[nblk_for(R)];
+            if (active) {
                 const int top = (lane == 0) ? topv : up;
-                int bmax[nblk_for(R)];
                 sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
                 prevTop = top;
                 bottom = c[R - 1];
-                if (hasDown) {
-                    if (lane == 31) st_volatile_u64(rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
-                } else if (A.bottom_row && lane == 31) A.bottom_row[jt] = bottom;
+            }
+            // The neighbour exchange for the NEXT step is issued the moment `bottom` exists: warps issue in order, so
+            // everything below (boundary-row store, arg-max bookkeeping, next step's fetches) now runs in the shadow of
+            // the shuffle latency instead of in front of it -- the step-to-step critical path is shuffle + R cells.
+            upN = __shfl_up_sync(0xffffffffu, bottom, 1);
+            if (MODE == 1) st_volatile_u64_if(writesRow, rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
+            else if (active) st_volatile_u64_if(writesRow, rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
+            if (active) {
                 if (LOCAL) {
                     const int colmax = max_of_blocks(bmax);
                     if (row0 + lane * R < m &&
@@ -279,6 +295,13 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             }
         }
     }
+}
+
+// bottom row of a row chunk: the last strip wrote it into its ring row as {4H, tag} words
+__global__ void long_bottom_row_kernel(const unsigned long long *row, int *bottom_row, const uint32_t n)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) bottom_row[j] = (int)(uint32_t)row[j];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -580,14 +580,18 @@ struct LongPlan {
     size_t strip_stride, row_stride, smem;
 };
 
-int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P)
+int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P, bool traceback = true)
 {
     const bool local = sc->mode == SA_LOCAL;
-    // Strip height: measured on B200 (tools/probe_r.py): R = 6 is fastest from 4 k to 100 k rows (the
-    // chain lag per strip, ~150 column-steps, outweighs the cheaper steps of smaller R); beyond that
-    // taller strips keep the number of resident warps near two per SM sub-partition.
+    // Strip height, measured on B200 (tools/probe_r.py, bench.py --workload c1..c3, bench_c5.py).  Fill alone:
+    // R = 8 is fastest from 4 k to 300 k rows (a step costs ~55 ns + 5 ns per row of the lane, the chain lag per
+    // strip is ~80 steps); beyond that the tallest strips win because every strip stays resident in one or two
+    // waves.  With the traceback the per-strip segment walks (32 R rows each, three passes) count as well, which
+    // favours lower strips for small matrices: 3.9 k x 3.7 k takes 1.30 / 1.31 / 1.64 ms at R = 4 / 6 / 8.
     (void)ctx;
-    int R = m <= 150000 ? 6 : m <= 300000 ? 8 : m <= 450000 ? 12 : 16;
+    int R = m <= 300000 ? 8 : m <= 450000 ? 12 : 16;
+    if (traceback && m <= 16000) R = 4;
+    else if (traceback && m <= 60000) R = 6;
     if (const char *e = std::getenv("SA_LONG_R")) {
         const int r = std::atoi(e);
         for (int k : kLongR) if (k == r) R = r;
@@ -675,7 +679,7 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
                  bool traceback, cudaStream_t st)
 {
     LongPlan P;
-    int rc = plan_long(ctx, sc, n, m, &P);
+    int rc = plan_long(ctx, sc, n, m, &P, traceback);
     if (rc) return rc;
     const bool local = sc->mode == SA_LOCAL;
     SA_TRY(ctx->dirs.reserve((size_t)P.n_strips * P.strip_stride * 4), SA_ERR_MEMORY);

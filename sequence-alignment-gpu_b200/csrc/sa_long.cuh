@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         uint32_t acc[NW];
 #pragma unroll
         for (int w = 0; w < NW; ++w) acc[w] = 0;
-        int upN = __shfl_up_sync(0xffffffffu, bottom, 1);
 
         // One wavefront step.  MODE 1 = steady state (every lane has a column, upkeep done by the
         // caller), MODE 2 = ramp-up (same, but lanes whose first column has not arrived yet idle),
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             const bool nextActive = MODE == 1 || (MODE == 2 ? jn >= 0 : (jn >= 0 && jn < n));
             const int letterN = nextActive ? (int)textWin[jn & 63] : 0;
             topN = topWin[k1 & (2 * PB - 1)];
-            const int up = upN;                     // exchanged right after the previous step's sweep
+            const int up = __shfl_up_sync(0xffffffffu, bottom, 1);
             const bool active = MODE == 1 || (MODE == 2 ? jt >= 0 : (jt >= 0 && jt < n));
             int bmax[nblk_for(R)];
             if (active) {
@@ -215,10 +214,8 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                 prevTop = top;
                 bottom = c[R - 1];
             }
-            // The neighbour exchange for the NEXT step is issued the moment `bottom` exists: warps issue in order, so
-            // everything below (boundary-row store, arg-max bookkeeping, next step's fetches) now runs in the shadow of
-            // the shuffle latency instead of in front of it -- the step-to-step critical path is shuffle + R cells.
-            upN = __shfl_up_sync(0xffffffffu, bottom, 1);
+            // (issuing the next step's shuffle here, right after the sweep, makes a lone strip 25 % faster but a long
+            // chain of strips slower -- 15.1 vs 14.2 ms at 100 k x 95 k -- so the exchange stays at the top of the step)
             if (MODE == 1) st_volatile_u64_if(writesRow, rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
             else if (active) st_volatile_u64_if(writesRow, rowOut + jt, (myTag << 32) | (unsigned long long)(uint32_t)bottom);
             if (active) {

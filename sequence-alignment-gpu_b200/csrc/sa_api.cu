@@ -633,8 +633,10 @@ int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, u
         if (const char *e = std::getenv("SA_TB_WD")) { const int w = std::atoi(e); if (w >= 1) Wd = w; }
         T.Wd = Wd; T.Q = (int)((n + Wd - 1) / Wd);
         {
-            // band of candidates around the predicted crossing: +-max(2048 columns, n/50)
-            const uint64_t half = std::max<uint64_t>(2048, n / 50);
+            // band of candidates around the predicted crossing: +-max(512 columns, n/50).  (A crossing outside the
+            // band only costs a serial segment; a wide band costs walkers far from the path, whose own paths run long
+            // gap stretches: +-2048 made the walkers 0.47 ms of a 1.3 ms call at 3.9 k x 3.7 k.)
+            const uint64_t half = std::max<uint64_t>(512, n / 50);
             int bq = (int)((half + Wd - 1) / Wd);
             if (const char *e = std::getenv("SA_TB_BAND")) { const int b = std::atoi(e); if (b >= 1) bq = b; }
             T.BQ = std::max(1, std::min(bq, std::max(1, T.Q / 2)));

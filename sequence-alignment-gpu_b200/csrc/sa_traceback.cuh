@@ -98,7 +98,10 @@ __device__ __forceinline__ int tb_tag(const TbLayout &L, TbCursor &cur, const in
 }
 
 // Follow the tags from (i, j) until row `stop_row` is reached (column 0 then runs straight up).
-__device__ __forceinline__ int tb_walk_to_row(const TbLayout &L, int i, int j, const int stop_row)
+// max_steps > 0 bounds the walk (speculative walkers only): a candidate far from the optimal path follows long gap
+// runs before it rejoins it; such a walker gives up and reports TB_UNKNOWN, which the resolver never matches.
+constexpr int TB_UNKNOWN = -1;
+__device__ __forceinline__ int tb_walk_to_row(const TbLayout &L, int i, int j, const int stop_row, int max_steps = 0)
 {
     TbCursor cur;
     while (i > stop_row) {
@@ -106,6 +109,7 @@ __device__ __forceinline__ int tb_walk_to_row(const TbLayout &L, int i, int j, c
         const int tag = tb_fetch(L, cur, i, j);
         i -= (tag != TAG_LEFT);
         j -= (tag != TAG_TOP);
+        if (max_steps > 0 && --max_steps == 0 && i > stop_row) return TB_UNKNOWN;
     }
     return j;
 }
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(128) tb_walkers_kernel(const TbArgs A)
     const int q = tb_band_q0(A, s) + qi;
     if (q > A.Q) return;
     const int c = min(q * A.Wd, A.Lay.n);
-    A.fa[(size_t)s * nb + qi] = (uint32_t)tb_walk_to_row(A.Lay, s * A.Lay.ROWS, c, (s - 1) * A.Lay.ROWS);
+    A.fa[(size_t)s * nb + qi] = (uint32_t)tb_walk_to_row(A.Lay, s * A.Lay.ROWS, c, (s - 1) * A.Lay.ROWS, 3 * A.Lay.ROWS + 64);
 }
 
 // ---- B: chain the lines ---------------------------------------------------------------------------
@@ -185,12 +189,9 @@ __global__ void tb_resolve_kernel(const TbArgs A)
                 nx = tb_walk_to_row(A.Lay, s * ROWS, x, (s - 1) * ROWS); ++fb;      // outside the band
             } else {
                 const uint32_t lo = A.fa[(size_t)s * nb + (q - q0)];
-                if (exact) nx = (int)lo;
-                else {
-                    const uint32_t hi = A.fa[(size_t)s * nb + (q + 1 - q0)];
-                    if (lo == hi) nx = (int)lo;                   // sandwiched between two merged paths
-                    else { nx = tb_walk_to_row(A.Lay, s * ROWS, x, (s - 1) * ROWS); ++fb; }
-                }
+                const uint32_t hi = exact ? lo : A.fa[(size_t)s * nb + (q + 1 - q0)];
+                if (lo == hi && lo != (uint32_t)TB_UNKNOWN) nx = (int)lo;     // exact hit, or sandwiched between two merged paths
+                else { nx = tb_walk_to_row(A.Lay, s * ROWS, x, (s - 1) * ROWS); ++fb; }
             }
         }
         x = nx;

@@ -41,6 +41,9 @@ def main():
     ap.add_argument("--chunks", type=int, default=1,
                     help="row chunks per slice; 1 = slices run one after the other.  (Measured: chunks do not pay with the "
                          "present kernel -- every launch still sweeps the whole slice width serially -- see DESIGN.md 6.)")
+    ap.add_argument("--linked", action="store_true",
+                    help="hand the border column over INSIDE the launches (peer memory through CUDA IPC, N >= 2): every "
+                         "rank launches its slice at once and the strips of neighbouring GPUs overlap")
     ap.add_argument("--check", action="store_true", help="also run the single-matrix path on rank 0 and compare (needs the memory)")
     args = ap.parse_args()
     import torch
@@ -78,7 +81,9 @@ def main():
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
-        if world > 1:
+        if world > 1 and args.linked:
+            res = strips.align_pair_strips_linked(eng, m, rank, world)
+        elif world > 1:
             res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer, chunks=args.chunks)
         else:
             res = strips.align_pair_strips_local([eng], m, chunks=args.chunks)
@@ -114,7 +119,8 @@ def main():
                               score=score, aln_len=len(at), checks=checks, dtype="int32", data="synthetic",
                               config=dict(workload=f"c5: NW {n} x {m} DNA, blast, gap 5", slices=world,
                                           row_chunks=args.chunks,
-                                          pipeline="rank k fills row chunk c while rank k+1 fills chunk c-1" if args.chunks > 1
+                                          pipeline="linked in-launch hand-off over peer memory (strips of neighbouring GPUs overlap)" if args.linked and world > 1
+                                          else "rank k fills row chunk c while rank k+1 fills chunk c-1" if args.chunks > 1
                                           else "slices run one after the other"))))
     if world > 1:
         dist.barrier()

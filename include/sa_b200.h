@@ -165,6 +165,23 @@ int sa_strip_begin(sa_context *ctx, const sa_scoring *scoring,
 int sa_strip_fill_rows(sa_context *ctx, uint64_t row0, uint64_t rows,
                        const int32_t *d_left_col, int32_t *d_right_col,
                        const int32_t *d_top_row, int32_t *d_bottom_row, int32_t *d_score, void *stream);
+/* Slices LINKED inside the launch (the pipelined multi-GPU wavefront): every GPU launches its slice at once; a
+ * strip of slice k+1 starts as soon as the same strip of slice k has written its right-most column into GPU k+1's
+ * border buffer -- plain 8-byte {4H, tag} stores over NVLink into memory mapped with CUDA IPC, polled locally.
+ *   sa_peer_alloc   a border buffer in this GPU's memory (>= 8*(pattern_len+1) bytes, zeroed) and its IPC handle
+ *   sa_peer_open    maps the RIGHT neighbour's buffer (handle from its sa_peer_alloc) into this process
+ *   sa_strip_fill_linked  after sa_strip_begin: the whole slice in one launch.  d_left_col64 = this rank's own border
+ *                   buffer (NULL for the first slice), d_right_col64 = the mapped buffer of the right neighbour (NULL
+ *                   for the last slice); tag != 0 identifies the call (same on all ranks, different every call).
+ *   sa_strip_linked_status  synchronises and reports SA_ERR_LAUNCH if a strip gave up waiting (~10 s) for a
+ *                   neighbour that never delivered. */
+int sa_peer_alloc(sa_context *ctx, uint64_t bytes, void **dptr, unsigned char handle[64]);
+int sa_peer_open(sa_context *ctx, const unsigned char handle[64], void **dptr);
+int sa_peer_close(sa_context *ctx, void *dptr);
+int sa_peer_free(sa_context *ctx, void *dptr);
+int sa_strip_fill_linked(sa_context *ctx, const uint64_t *d_left_col64, uint64_t *d_right_col64, uint32_t tag,
+                         int32_t *d_score, void *stream);
+int sa_strip_linked_status(sa_context *ctx, void *stream);
 int sa_strip_traceback(sa_context *ctx, uint64_t start_row,
                        char *d_aligned_text, char *d_aligned_pattern, uint64_t cap,
                        uint64_t *d_result4, void *stream);

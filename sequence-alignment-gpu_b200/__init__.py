@@ -131,6 +131,12 @@ def lib() -> C.CDLL:
                                      C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
         L.sa_strip_fill_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+        L.sa_peer_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+        L.sa_peer_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.sa_peer_close.argtypes = [C.c_void_p, C.c_void_p]
+        L.sa_peer_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.sa_strip_fill_linked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.sa_strip_linked_status.argtypes = [C.c_void_p, C.c_void_p]
         L.sa_strip_traceback.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.sa_validate_and_transform.restype = C.c_int64
         L.sa_validate_and_transform.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_char_p]
@@ -260,6 +266,31 @@ class Aligner:
                                                C.c_void_p(d_right_col or None), C.c_void_p(d_top_row or None),
                                                C.c_void_p(d_bottom_row or None), C.c_void_p(d_score or None),
                                                C.c_void_p(stream)))
+
+    # -- slices linked inside the launch (peer border buffers through CUDA IPC)
+    def peer_alloc(self, nbytes):
+        """-> (device pointer, 64-byte IPC handle) of a zeroed border buffer in this GPU's memory."""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self._check(self._L.sa_peer_alloc(self._ctx, int(nbytes), C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def peer_open(self, handle: bytes):
+        ptr = C.c_void_p()
+        self._check(self._L.sa_peer_open(self._ctx, handle, C.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, ptr):
+        self._check(self._L.sa_peer_close(self._ctx, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        self._check(self._L.sa_peer_free(self._ctx, C.c_void_p(ptr)))
+
+    def strip_fill_linked(self, d_left_col64, d_right_col64, tag, d_score=0, stream=0):
+        self._check(self._L.sa_strip_fill_linked(self._ctx, C.c_void_p(d_left_col64 or None), C.c_void_p(d_right_col64 or None),
+                                                 int(tag), C.c_void_p(d_score or None), C.c_void_p(stream)))
+
+    def strip_linked_status(self, stream=0):
+        self._check(self._L.sa_strip_linked_status(self._ctx, C.c_void_p(stream)))
 
     def strip_traceback(self, start_row, d_out_text, d_out_pattern, cap, d_result4, stream=0):
         self._check(self._L.sa_strip_traceback(self._ctx, int(start_row), d_out_text, d_out_pattern, int(cap), d_result4,

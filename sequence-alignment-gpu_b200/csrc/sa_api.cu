@@ -98,6 +98,7 @@ struct sa_context {
         const uint8_t *d_text = nullptr, *d_pat = nullptr;
         uint64_t n = 0, m = 0, col0 = 0, total = 0, chunk = 0;
         size_t row_stride = 0, smem = 0;
+        uint32_t dbg_strips = 0;
         int gap = 0;
         char alphabet[40] = {};
     } strip;
@@ -536,20 +537,25 @@ constexpr int LONG_WARPS = 4;
 const int kLongR[] = {2, 4, 6, 8, 12, 16};
 
 template <int R>
+const void *long_kernel_fn(bool local, bool linked)
+{
+    return local ? (const void *)long_fill_kernel<R, true, LONG_WARPS, false>
+                 : linked ? (const void *)long_fill_kernel<R, false, LONG_WARPS, true> : (const void *)long_fill_kernel<R, false, LONG_WARPS, false>;
+}
+template <int R>
 cudaError_t launch_long_t(const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
 {
     void *args[] = {(void *)&A};
-    cudaError_t e;
-    const void *fn = local ? (const void *)long_fill_kernel<R, true, LONG_WARPS> : (const void *)long_fill_kernel<R, false, LONG_WARPS>;
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void *fn = long_kernel_fn<R>(local, A.left_col64 || A.right_col64 || A.dbg);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LONG_WARPS * 32), args, smem, st);
 }
 template <int R>
-int occupancy_long_t(bool local, size_t smem)
+int occupancy_long_t(bool local, size_t smem, bool linked)
 {
     int nb = 0;
-    const void *fn = local ? (const void *)long_fill_kernel<R, true, LONG_WARPS> : (const void *)long_fill_kernel<R, false, LONG_WARPS>;
+    const void *fn = long_kernel_fn<R>(local, linked);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, LONG_WARPS * 32, smem);
     return nb;
@@ -568,9 +574,9 @@ cudaError_t launch_long(int R, const LongArgs &A, bool local, int grid, size_t s
     LONG_DISPATCH(launch_long_t, A, local, grid, smem, st);
     return cudaErrorInvalidValue;
 }
-int occupancy_long(int R, bool local, size_t smem)
+int occupancy_long(int R, bool local, size_t smem, bool linked = false)
 {
-    LONG_DISPATCH(occupancy_long_t, local, smem);
+    LONG_DISPATCH(occupancy_long_t, local, smem, linked);
     return 0;
 }
 
@@ -1058,20 +1064,104 @@ int sa_strip_begin(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text,
     return SA_OK;
 }
 
+static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int32_t *d_left_col, int32_t *d_right_col,
+                        const int32_t *d_top_row, int32_t *d_bottom_row, const unsigned long long *d_left64,
+                        unsigned long long *d_right64, uint32_t xtag, int32_t *d_score, void *stream);
+
 int sa_strip_fill_rows(sa_context *ctx, uint64_t row0, uint64_t rows, const int32_t *d_left_col, int32_t *d_right_col,
                        const int32_t *d_top_row, int32_t *d_bottom_row, int32_t *d_score, void *stream)
+{
+    if (!ctx || !ctx->strip.valid) return SA_ERR_ARGUMENT;
+    if ((ctx->strip.col0 == 0) != (d_left_col == nullptr)) return SA_ERR_ARGUMENT;
+    return strip_launch(ctx, row0, rows, d_left_col, d_right_col, d_top_row, d_bottom_row, nullptr, nullptr, 0, d_score, stream);
+}
+
+// ---- slices linked inside the launch: peer buffers through CUDA IPC ------------------------------------------
+int sa_peer_alloc(sa_context *ctx, uint64_t bytes, void **dptr, unsigned char handle[64])
+{
+    if (!ctx || !dptr || !handle || bytes == 0) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    SA_TRY(cudaMalloc(&p, bytes), SA_ERR_MEMORY);
+    SA_TRY(cudaMemset(p, 0, bytes), SA_ERR_LAUNCH);
+    cudaIpcMemHandle_t h;
+    SA_TRY(cudaIpcGetMemHandle(&h, p), SA_ERR_LAUNCH);
+    std::memcpy(handle, &h, 64);
+    *dptr = p;
+    return SA_OK;
+}
+int sa_peer_open(sa_context *ctx, const unsigned char handle[64], void **dptr)
+{
+    if (!ctx || !dptr || !handle) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    SA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess), SA_ERR_LAUNCH);
+    return SA_OK;
+}
+int sa_peer_close(sa_context *ctx, void *dptr)
+{
+    if (!ctx || !dptr) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    SA_TRY(cudaIpcCloseMemHandle(dptr), SA_ERR_LAUNCH);
+    return SA_OK;
+}
+int sa_peer_free(sa_context *ctx, void *dptr)
+{
+    if (!ctx || !dptr) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    SA_TRY(cudaFree(dptr), SA_ERR_LAUNCH);
+    return SA_OK;
+}
+
+// The whole slice in one launch; the border column arrives in d_left_col64 (this GPU's memory, pattern_len+1 words
+// {4H, tag}, written by the left neighbour's kernel; NULL for the first slice) and the right-most column is written
+// into d_right_col64 (the right neighbour's buffer opened with sa_peer_open; NULL for the last slice).  `tag` must
+// be the same on every rank and differ from call to call.
+int sa_strip_fill_linked(sa_context *ctx, const uint64_t *d_left_col64, uint64_t *d_right_col64, uint32_t tag,
+                         int32_t *d_score, void *stream)
+{
+    if (!ctx || !ctx->strip.valid || tag == 0) return SA_ERR_ARGUMENT;
+    if ((ctx->strip.col0 == 0) != (d_left_col64 == nullptr)) return SA_ERR_ARGUMENT;
+    return strip_launch(ctx, 0, ctx->strip.m, nullptr, nullptr, nullptr, nullptr,
+                        reinterpret_cast<const unsigned long long *>(d_left_col64),
+                        reinterpret_cast<unsigned long long *>(d_right_col64), tag, d_score, stream);
+}
+
+// SA_OK, or SA_ERR_LAUNCH when a strip of the last linked fill gave up waiting for its neighbour (synchronises).
+int sa_strip_linked_status(sa_context *ctx, void *stream)
+{
+    if (!ctx || !ctx->strip.valid) return SA_ERR_ARGUMENT;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
+    int flag = 0;
+    SA_TRY(cudaMemcpyAsync(&flag, ctx->misc.as<char>() + 56, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream), SA_ERR_COPY);
+    SA_TRY(cudaStreamSynchronize((cudaStream_t)stream), SA_ERR_LAUNCH);
+    if (const char *path = std::getenv("SA_LONG_DBG")) {
+        std::vector<unsigned long long> h((size_t)ctx->strip.dbg_strips * 3);
+        if (!h.empty() && cudaMemcpy(h.data(), ctx->tbbuf.p, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            char name[512];
+            std::snprintf(name, sizeof name, "%s.dev%d", path, ctx->device);
+            if (FILE *f = std::fopen(name, "wb")) { std::fwrite(h.data(), 8, h.size(), f); std::fclose(f); }
+        }
+    }
+    return flag ? SA_ERR_LAUNCH : SA_OK;
+}
+
+static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int32_t *d_left_col, int32_t *d_right_col,
+                        const int32_t *d_top_row, int32_t *d_bottom_row, const unsigned long long *d_left64,
+                        unsigned long long *d_right64, uint32_t xtag, int32_t *d_score, void *stream)
 {
     if (!ctx || !ctx->strip.valid || rows == 0) return SA_ERR_ARGUMENT;
     auto &S = ctx->strip;
     const uint64_t ROWS = 32ull * S.R;
     const bool last = row0 + rows == S.m;
     if (row0 + rows > S.m || row0 % ROWS != 0 || (!last && rows % ROWS != 0)) return SA_ERR_ARGUMENT;
-    if ((S.col0 == 0) != (d_left_col == nullptr)) return SA_ERR_ARGUMENT;
     if ((row0 == 0) != (d_top_row == nullptr) || (!last && !d_bottom_row)) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t nStrips = (uint32_t)((rows + ROWS - 1) / ROWS);
-    int occ = occupancy_long(S.R, false, S.smem);
+    int occ = occupancy_long(S.R, false, S.smem, d_left64 || d_right64 || std::getenv("SA_LONG_DBG"));
     if (occ < 1) return SA_ERR_LAUNCH;
     const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
     const int grid = (int)std::min<uint64_t>(maxBlocks, (nStrips + LONG_WARPS - 1) / LONG_WARPS);
@@ -1093,6 +1183,15 @@ int sa_strip_fill_rows(sa_context *ctx, uint64_t row0, uint64_t rows, const int3
     A.n_strips = nStrips; A.left_col = d_left_col ? d_left_col + row0 : nullptr;
     A.right_col = d_right_col ? d_right_col + row0 : nullptr; A.col0 = (uint32_t)S.col0;
     A.row_base = (uint32_t)row0; A.top_row = d_top_row; A.bottom_row = last ? nullptr : d_bottom_row;
+    A.left_col64 = d_left64; A.right_col64 = d_right64; A.xtag = xtag;
+    A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);
+    if (d_left64 || d_right64) SA_TRY(cudaMemsetAsync(A.abort_flag, 0, 4, st), SA_ERR_LAUNCH);
+    if (std::getenv("SA_LONG_DBG")) {          // dev aid: per-strip timestamps, dumped by sa_strip_linked_status
+        SA_TRY(ctx->tbbuf.reserve((size_t)nStrips * 24 + 64), SA_ERR_MEMORY);
+        SA_TRY(cudaMemsetAsync(ctx->tbbuf.p, 0, (size_t)nStrips * 24, st), SA_ERR_LAUNCH);
+        A.dbg = ctx->tbbuf.as<unsigned long long>();
+        ctx->strip.dbg_strips = nStrips;
+    }
     A.score = d_score ? d_score : reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 32);
     A.tag_base = (uint32_t)ctx->epoch << 21;
     A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);

@@ -38,6 +38,17 @@ struct LongArgs {
     uint32_t row_base;
     const int *top_row;
     int *bottom_row;
+    // Slices LINKED inside the launch (the multi-GPU wavefront): the border column is a buffer of 64-bit
+    // {4*H(i, col0), tag} words in THIS GPU's memory that the left neighbour's kernel fills over NVLink with plain
+    // 8-byte stores (right_col64 is the peer's buffer, mapped through CUDA IPC).  A strip polls its own rows before
+    // it starts and publishes its right-most column when it ends, so GPU k works on strip s while GPU k+1 works on
+    // strip s-1 -- the cross-GPU analogue of the strip ring.  xtag identifies the call; abort_flag (device int) is
+    // raised by a strip that waited longer than the limit (dead neighbour) and makes every other wait give up.
+    const unsigned long long *left_col64;
+    unsigned long long *right_col64;
+    uint32_t xtag;
+    int *abort_flag;
+    unsigned long long *dbg;       // optional: per strip {start ns, border-ready ns, end ns} (globaltimer)
     // results
     int32_t *score;          // NW: H(m, n) of this slice
     int *cand_v; uint32_t *cand_i; uint32_t *cand_j;   // SW: per-strip arg-max candidates
@@ -64,7 +75,9 @@ __device__ __forceinline__ void st_volatile_u64_if(const bool pred, unsigned lon
 
 constexpr int PB = 8;   // boundary-row prefetch block (columns)
 
-template <int R, bool LOCAL, int WARPS>
+// LINKED: the variant with the cross-GPU border hand-off and the per-strip timestamps compiled in (kept out of the
+// plain kernel: even outside the step loop the extra code costs it ~5 % through register allocation).
+template <int R, bool LOCAL, int WARPS, bool LINKED = false>
 __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
@@ -110,19 +123,42 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         __syncwarp();
 
         // ---- boundary state (left border of the slice) ----
+        // linked slices: wait until the left neighbour's kernel has delivered the word (tag == xtag)
+        auto linked_border = [&](const int gi) -> int {
+            if (gi == 0) return LOCAL ? 0 : -SCALE * A.gap * (int)A.col0;
+            if (gi > m) return 0;
+            unsigned long long v = ld_volatile_u64(A.left_col64 + gi);
+            const long long t0 = clock64();
+            for (unsigned it = 1; (uint32_t)(v >> 32) != A.xtag; ++it) {
+                // (the shared abort word is looked at rarely: thousands of waiting lanes reading ONE address every
+                // microsecond saturate its L2 slice and slow the strips that are already running)
+                if ((it & 1023u) == 0) {
+                    if (*reinterpret_cast<volatile int *>(A.abort_flag)) break;
+                    if (clock64() - t0 > 20000000000ll) { atomicExch(A.abort_flag, 1); break; }     // ~10 s: the neighbour is gone
+                }
+                __nanosleep(2000);
+                v = ld_volatile_u64(A.left_col64 + gi);
+            }
+            return (int)(uint32_t)v;
+        };
+        auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+        if (LINKED && A.dbg && lane == 0) A.dbg[3 * s] = gtime();
         int c[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int gi = row0 + lane * R + r + 1;     // DP row
-            if (A.left_col) c[r] = gi <= m ? A.left_col[gi] : 0;
+            if (LINKED && A.left_col64) c[r] = linked_border(gi);
+            else if (A.left_col) c[r] = gi <= m ? A.left_col[gi] : 0;
             else c[r] = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
         }
         int prevTop;                                    // 4*H(i0-1, col0)
         {
             const int gi = row0 + lane * R;
-            if (A.left_col) prevTop = gi <= m ? A.left_col[gi] : 0;
+            if (LINKED && A.left_col64) prevTop = linked_border(gi);
+            else if (A.left_col) prevTop = gi <= m ? A.left_col[gi] : 0;
             else prevTop = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
         }
+        if (LINKED && A.dbg) { __syncwarp(); if (lane == 0) A.dbg[3 * s + 1] = gtime(); }
         int bottom = 0;
         int bestv = 0, besti = 0, bestj = 0;
         int gmCached = 0;                               // lane-local copy of *A.gmax (a lower bound)
@@ -262,6 +298,14 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         }
 
         // ---- strip results ----
+        if (LINKED && A.dbg && lane == 0) A.dbg[3 * s + 2] = gtime();
+        if (LINKED && A.right_col64) {          // linked slices: straight into the right neighbour's memory
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int gi = row0 + lane * R + r + 1;
+                if (gi <= m) st_volatile_u64(A.right_col64 + gi, ((unsigned long long)A.xtag << 32) | (unsigned long long)(uint32_t)c[r]);
+            }
+        }
         if (A.right_col) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {

@@ -85,6 +85,33 @@ class GpuStripEngine:
                                 bottom_row.data_ptr() if bottom_row is not None else 0, self.d_score.data_ptr(),
                                 stream=self.stream.cuda_stream)
 
+    # -- slices linked inside the launch: border buffers in peer memory (CUDA IPC), no host hand-off at all
+    def linked_setup(self):
+        """Allocates this slice's border buffer ({4H, tag} words); returns its IPC handle for the LEFT neighbour."""
+        if not hasattr(self, "border_ptr"):
+            self.border_ptr, self.border_handle = self.al.peer_alloc(8 * (self.m + 1))
+            self.right_ptr = 0
+        return self.border_handle
+
+    def linked_connect(self, right_handle=None, right_ptr=None):
+        """right_handle: IPC handle of the right neighbour's border buffer (another process); right_ptr: its device
+        pointer when the neighbour lives in this process (tests on one GPU)."""
+        self.right_ptr = self.al.peer_open(right_handle) if right_handle is not None else (right_ptr or 0)
+
+    def fill_linked(self, tag):
+        torch = self.torch
+        self.begin(0)
+        self._e0, self._e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            self._e0.record()
+            self.al.strip_fill_linked(self.border_ptr if self.col0 > 0 else 0, self.right_ptr, tag, self.d_score.data_ptr(),
+                                      stream=self.stream.cuda_stream)
+            self._e1.record()
+
+    def linked_finish(self):
+        self.al.strip_linked_status(stream=self.stream.cuda_stream)       # synchronises; raises if a neighbour never delivered
+        self.fill_ms = self._e0.elapsed_time(self._e1)
+
     def score(self):
         return int(self.d_score.item())
 
@@ -160,6 +187,59 @@ def fill_slice_pipelined(engine, m, rank: int, world: int, make_column, chunks: 
             top, row0, c = bottom, row0 + rows, c + 1
     engine._keep = (left, right, rows_bufs)
     return right
+
+
+_linked_calls = [0]
+
+
+def align_pair_strips_linked(engine, m, rank: int, world: int, group=None):
+    """One slice per rank, linked inside the launches (GpuStripEngine only): every rank launches its whole slice at
+    once; strip s of rank k+1 starts when strip s of rank k has written its right-most column into rank k+1's border
+    buffer over NVLink.  Returns like align_pair_strips."""
+    import torch
+    import torch.distributed as dist
+    if not hasattr(engine, "right_ptr"):
+        handles = [None] * world
+        dist.all_gather_object(handles, engine.linked_setup(), group=group)
+        engine.linked_connect(right_handle=handles[rank + 1] if rank + 1 < world else None)
+    _linked_calls[0] += 1
+    dist.barrier(group=group)                 # every border buffer exists and is mapped before anyone writes
+    engine.fill_linked(_linked_calls[0])
+    engine.linked_finish()
+    row_t = torch.zeros(1, dtype=torch.int64, device=engine.dev)
+    if rank + 1 < world:
+        dist.recv(row_t, src=rank + 1, group=group)
+        row = int(row_t.item())
+    else:
+        row = m
+    t, p, row, ti, pi = engine.traceback(row)
+    score = engine.score()
+    if rank > 0:
+        row_t.fill_(row)
+        dist.send(row_t, dst=rank - 1, group=group)
+    parts = [None] * world
+    dist.all_gather_object(parts, (t, p, ti, pi, score), group=group)
+    return (parts[-1][4], b"".join(x[0] for x in parts), b"".join(x[1] for x in parts), parts[0][2], parts[0][3])
+
+
+def align_pair_strips_linked_local(engines, m, tag=1):
+    """The linked protocol with all slices in ONE process on one GPU (tests): the kernels cannot run side by side
+    there, so they are launched left to right, each finding its border already delivered."""
+    live = [e for e in engines if e.n > 0]
+    for e in live:
+        e.linked_setup()
+    for e, nxt in zip(live, live[1:] + [None]):
+        e.linked_connect(right_ptr=nxt.border_ptr if nxt is not None else 0)
+    for e in live:
+        e.fill_linked(tag)
+        e.linked_finish()
+    score = live[-1].score()
+    row, pieces, ti, pi = m, [], 0, 0
+    for e in reversed(live):
+        t, p, row, ti, pi = e.traceback(row)
+        pieces.append((t, p))
+    pieces.reverse()
+    return score, b"".join(t for t, _ in pieces), b"".join(p for _, p in pieces), ti, pi
 
 
 def align_pair_strips(engine, m, rank: int, world: int, make_column, group=None, chunks: int = 1):

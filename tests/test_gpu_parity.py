@@ -288,6 +288,33 @@ def test_column_slices_vs_oracle(sa, oracle, monkeypatch, world, tb):
     assert_same(_strip_align(sa, 4, blast, 5, t, p, world), oracle.align(0, 4, blast, 5, t, p), (world, "ties"))
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_linked_slices_vs_oracle(sa, oracle, world):
+    """The in-launch hand-off of the border column ({4H, tag} words in the neighbour's buffer, sa_strip_fill_linked):
+    same result as the oracle.  On one GPU the slices are launched left to right (the protocol, not the overlap)."""
+    from sa_b200 import strips
+    rng = np.random.default_rng(300 + world)
+    blast = helpers.matrices()["dna/blast.txt"]
+    for n, m in ((2500, 2300), (900, 1700), (12, 7)):
+        import synth
+        t = rng.integers(0, 4, n, dtype=np.uint8)
+        base = synth.mutate_indices_numpy(t, rng, 4)
+        p = base[:m] if m <= len(base) else np.concatenate((base, rng.integers(0, 4, m - len(base), dtype=np.uint8)))
+        als = [sa.Aligner(0) for _ in range(world)]
+        try:
+            eng = [strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, len(t), p)
+                   for al, (c0, w) in zip(als, strips.slice_columns(len(t), world))]
+            for tag in (1, 2):          # twice: the tags of the first call must not satisfy the second
+                score, at, ap, ti, pi = strips.align_pair_strips_linked_local(eng, len(p), tag=tag)
+                assert_same(sa.Alignment(score, len(at), ti, pi, at, ap), oracle.align(0, 4, blast, 5, t, p), (world, n, m, tag))
+            for e in eng:
+                if hasattr(e, "border_ptr"):
+                    e.al.peer_free(e.border_ptr)
+        finally:
+            for al in als:
+                al.close()
+
+
 def test_column_slices_full_size_c3(sa, aligner):
     """The slice path on the 100 000 x 95 217 pair (4 slices): same answer as the single-matrix path and
     the reference's known answer for this pair."""

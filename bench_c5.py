@@ -41,9 +41,11 @@ def main():
     ap.add_argument("--chunks", type=int, default=1,
                     help="row chunks per slice; 1 = slices run one after the other.  (Measured: chunks do not pay with the "
                          "present kernel -- every launch still sweeps the whole slice width serially -- see DESIGN.md 6.)")
-    ap.add_argument("--linked", action="store_true",
-                    help="hand the border column over INSIDE the launches (peer memory through CUDA IPC, N >= 2): every "
-                         "rank launches its slice at once and the strips of neighbouring GPUs overlap")
+    ap.add_argument("--no-linked", dest="linked", action="store_false",
+                    help="default (N >= 2): the border column is handed over INSIDE the launches (peer memory through CUDA "
+                         "IPC; every rank launches its slice at once and the strips of neighbouring GPUs overlap).  With "
+                         "--no-linked the slices run one after the other with NCCL send/recv of the whole column")
+    ap.set_defaults(linked=True)
     ap.add_argument("--check", action="store_true", help="also run the single-matrix path on rank 0 and compare (needs the memory)")
     args = ap.parse_args()
     import torch

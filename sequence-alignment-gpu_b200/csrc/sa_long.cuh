@@ -124,25 +124,30 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
 
         // ---- boundary state (left border of the slice) ----
         // linked slices: wait until the left neighbour's kernel has delivered the word (tag == xtag)
-        auto linked_border = [&](const int gi) -> int {
-            if (gi == 0) return LOCAL ? 0 : -SCALE * A.gap * (int)A.col0;
-            if (gi > m) return 0;
-            unsigned long long v = ld_volatile_u64(A.left_col64 + gi);
-            const long long t0 = clock64();
-            for (unsigned it = 1; (uint32_t)(v >> 32) != A.xtag; ++it) {
-                // (the shared abort word is looked at rarely: thousands of waiting lanes reading ONE address every
-                // microsecond saturate its L2 slice and slow the strips that are already running)
-                if ((it & 1023u) == 0) {
-                    if (*reinterpret_cast<volatile int *>(A.abort_flag)) break;
-                    if (clock64() - t0 > 20000000000ll) { atomicExch(A.abort_flag, 1); break; }     // ~10 s: the neighbour is gone
-                }
-                __nanosleep(2000);
-                v = ld_volatile_u64(A.left_col64 + gi);
-            }
-            return (int)(uint32_t)v;
-        };
+        // The wait is WARP-UNIFORM (all lanes leave the loop together on a vote).  A per-lane loop -- every lane
+        // spinning on its own word -- leaves the warp split into lane groups that the later __syncwarp / shuffles
+        // synchronise but do not merge again: such a strip then issues every instruction once per group and sweeps
+        // 3.4x slower for its whole life (seen as activemask 0xff00ffff after the steady loop), and the chain queues
+        // up behind it.
         auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
         if (LINKED && A.dbg && lane == 0) A.dbg[3 * s] = gtime();
+        auto linked_border = [&](const int gi) -> int {
+            const bool need = gi > 0 && gi <= m;
+            unsigned long long v = need ? ld_volatile_u64(A.left_col64 + gi) : 0ull;
+            const long long t0 = clock64();
+            for (unsigned it = 1;; ++it) {
+                const bool ok = !need || (uint32_t)(v >> 32) == A.xtag;
+                if (__all_sync(0xffffffffu, ok)) break;
+                if ((it & 1023u) == 0) {      // rarely: thousands of lanes reading ONE word every microsecond would saturate its L2 slice
+                    bool dead = *reinterpret_cast<volatile int *>(A.abort_flag) != 0;
+                    if (clock64() - t0 > 20000000000ll) { atomicExch(A.abort_flag, 1); dead = true; }     // ~10 s: the neighbour is gone
+                    if (__any_sync(0xffffffffu, dead)) break;
+                }
+                __nanosleep(1000);
+                if (!ok) v = ld_volatile_u64(A.left_col64 + gi);
+            }
+            return gi == 0 ? (LOCAL ? 0 : -SCALE * A.gap * (int)A.col0) : (int)(uint32_t)v;
+        };
         int c[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                 step(k + k8, k8 % CB, std::integral_constant<int, 1>{});
             }
         }
+        if (LINKED && A.dbg) { const unsigned am = __activemask(); if (lane == 0) A.dbg[3 * A.n_strips + s] = am; }
         for (; k < nStepsPad; k += CB) {
 #pragma unroll
             for (int kk = 0; kk < CB; ++kk) step(k + kk, kk, std::integral_constant<int, 0>{});

@@ -9,12 +9,16 @@ direction words of that slice (a 1 M x 1 M pair needs 250 GB of directions: 125 
              its left edge (sa_strip_traceback) and hands the row to the rank on its left.
   result     the aligned strings are the concatenation of the pieces in rank order.
 
-The only communication is point-to-point between neighbours (torch.distributed send/recv: NCCL over
-NVLink between GPUs, gloo in the CPU tests).  By default the slices run one after the other (a rank starts
-when the whole column of its left neighbour has arrived).  The row-chunk protocol (chunks > 1,
-sa_strip_fill_rows) hands the column over piecewise so that neighbours could overlap; it is exact and
-tested, but with the present kernel every launch sweeps the whole slice width serially, so K chunks cost
-K sweeps and it is slower -- the overlap needs the hand-off INSIDE one persistent launch.
+Two ways of handing the border column over:
+
+  linked (align_pair_strips_linked, the default of bench_c5.py): every rank launches its whole slice at once; a
+      strip of slice k+1 starts when the same strip of slice k has written its right-most column into rank k+1's
+      border buffer -- plain 8-byte {4H, tag} stores over NVLink into memory mapped with CUDA IPC, polled locally.
+      Neighbouring GPUs overlap: 1 M x 951 k takes 0.325 s on 2 GPUs, 0.278 s on 4.
+  sequential (align_pair_strips): torch.distributed send/recv of the whole column (NCCL between GPUs, gloo in the
+      CPU tests); a rank starts when its left neighbour has finished (0.44 s).  The row-chunk variant of it
+      (chunks > 1, sa_strip_fill_rows) is exact and tested but slower with the present kernel: every launch sweeps
+      the whole slice width serially, so K chunks cost K sweeps.
 
 `engine` is anything with fill(left_col) -> right_col, score(), traceback(start_row): GpuStripEngine
 below for the product path; the CPU tests plug in a numpy restatement.

@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -418,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4"])

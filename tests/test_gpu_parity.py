@@ -369,3 +369,22 @@ def test_reference_gpu_path_agrees(aligner):
     for mode, alpha, mat, n in ((0, 4, blast, 700), (1, 4, blast, 900), (0, 23, b50, 1200), (1, 23, b50, 2500)):
         t, p = helpers.random_case(rng, alpha, n)
         assert_same(aligner.align(mode, alpha, mat, 5, t, p), ref.align(mode, alpha, mat, 5, t, p), ("reference GPU", mode, alpha, n))
+
+
+def test_linked_slices_two_gpus(sa):
+    """The real thing on two GPUs (skipped on a one-GPU box): two processes, CUDA IPC border buffers, both slices
+    launched at once; rank 0 also runs the single-matrix path and compares (bench_c5.py --check)."""
+    import json
+    import subprocess
+    import sys
+    if sa.lib().sa_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(root, "bench_c5.py"), "--length", "60000", "--steps", "2", "--check"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and "linked" in line["config"]["pipeline"]
+    assert all(v is True for k, v in line["checks"].items() if k != "starts"), line["checks"]
+    assert line["checks"]["equals_single_matrix_path"] is True

@@ -388,3 +388,27 @@ def test_linked_slices_two_gpus(sa):
     assert line["n_gpus"] == 2 and "linked" in line["config"]["pipeline"]
     assert all(v is True for k, v in line["checks"].items() if k != "starts"), line["checks"]
     assert line["checks"]["equals_single_matrix_path"] is True
+
+
+@pytest.mark.parametrize("gap", [0, 1, 31, 32, 40, 300])
+def test_gap_penalty_extremes(sa, aligner, oracle, force_path, gap):
+    """Gap penalties at the edges of the fast paths: 0 (ties everywhere, sentinel columns do not decay), 31 / 32 (the NW
+    form of the straight-line batch kernel needs 4*gap - 128 < 2), 40 and 300 (s16 guard -> s32 kernels).  Single pairs
+    through both kernels and a batch, both modes, against the oracle."""
+    rng = np.random.default_rng(900 + gap)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+    for path in ("batch", "long"):
+        force_path(path)
+        for mode in (0, 1):
+            for alpha, mat in ((4, blast), (23, b62)):
+                t, p = helpers.random_case(rng, alpha, 330)
+                assert_same(aligner.align(mode, alpha, mat, gap, t, p), oracle.align(mode, alpha, mat, gap, t, p), (path, mode, alpha, gap))
+    force_path(None)
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(300, seed=gap + 1, lo=200, hi=340)
+    for mode in (0, 1):
+        out = aligner.align_batch(mode, 23, b62, gap, T, toff, P, poff)
+        for i in range(0, 300, 7):
+            want = oracle.align(mode, 23, b62, gap, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]])
+            assert_same(sa.unpack_batch(out, i), want, ("batch", mode, gap, i))

@@ -37,7 +37,8 @@ typedef enum {
     SA_ERR_MEMORY = -2,      /* device or pinned allocation failed (reference: MEM_ERROR, alignSequenceGPU.cu:541-546) */
     SA_ERR_COPY = -3,        /* host<->device copy failed (reference: "could not copy from device memory", :588-594) */
     SA_ERR_ARGUMENT = -4,    /* null pointer, empty sequence, residue >= alphabet_size, alphabet_size > 32 ... */
-    SA_ERR_SCORE_RANGE = -5, /* |score| or gap too large for the packed arithmetic (see DESIGN.md "ranges") */
+    SA_ERR_SCORE_RANGE = -5, /* |score| > 4064 or gap > 2^24; also: a matrix beyond +-31 given to the device-resident
+                              * batch / slice entry points (such matrices run through the single-pair kernels only) */
     SA_ERR_LAUNCH = -6,      /* kernel launch / execution error */
     SA_ERR_CAPACITY = -7     /* caller-provided output buffer too small */
 } sa_status;

@@ -88,6 +88,7 @@ struct sa_context {
     PinBuf pin;
     Slot slot[NSLOT];
     uint32_t epoch = 0;
+    bool wide = false;                      // the scoring uploaded last needs the two-plane profile
     size_t rowbuf_entries_valid = 0;
     // column-slice state of sa_strip_fill, consumed by sa_strip_traceback
     struct StripState {
@@ -143,6 +144,18 @@ void reset_timing(sa_context *ctx)
 }
 
 // ------------------------------------------------------------------ scoring tables
+// Scores beyond +-31 do not fit the one-byte profile of the packed kernels: such matrices run through the long-pair
+// kernel with a two-plane profile (sweep_column_wide), whatever the pair size.
+bool scoring_is_wide(const sa_scoring *sc)
+{
+    if (!sc || !sc->score_matrix) return false;
+    const int a = sc->alphabet_size;
+    if (a < 1 || a > MAX_ALPHA) return false;
+    for (int i = 0; i < a * a; ++i)
+        if (sc->score_matrix[i] * SCALE < -127 || sc->score_matrix[i] * SCALE > 127) return true;
+    return false;
+}
+
 int upload_scoring(sa_context *ctx, const sa_scoring *sc, cudaStream_t st)
 {
     if (!sc || !sc->score_matrix || !sc->alphabet) return SA_ERR_ARGUMENT;
@@ -150,16 +163,26 @@ int upload_scoring(sa_context *ctx, const sa_scoring *sc, cudaStream_t st)
     if (sc->mode != SA_GLOBAL && sc->mode != SA_LOCAL) return SA_ERR_ARGUMENT;
     if (sc->gap < 0 || sc->gap > (1 << 24)) return SA_ERR_SCORE_RANGE;
     const int a = sc->alphabet_size;
-    int8_t h4[32 * MAX_ALPHA];
+    // 4*S as bytes for IDP.4A: one plane when every |4*S| <= 127; otherwise ("wide" scoring, long-pair kernel only)
+    // 4*S = 128*hi + lo with lo in 0..127 in the first plane and the signed hi in the second
+    int8_t h4[2 * 32 * MAX_ALPHA];
     int32_t hs[MAX_ALPHA * MAX_ALPHA];
     std::memset(h4, 0, sizeof h4);
+    const bool wide = scoring_is_wide(sc);
     for (int p = 0; p < a; ++p)
         for (int t = 0; t < a; ++t) {
             const int v = sc->score_matrix[p * a + t];
-            if (v * SCALE < -127 || v * SCALE > 127) return SA_ERR_SCORE_RANGE;   // IDP.4A byte profile
-            h4[p * 32 + t] = (int8_t)(v * SCALE);
+            if (v < -4064 || v > 4064) return SA_ERR_SCORE_RANGE;
+            const int v4 = v * SCALE;
+            if (!wide) h4[p * 32 + t] = (int8_t)v4;
+            else {
+                const int lo = v4 & 127;
+                h4[p * 32 + t] = (int8_t)lo;
+                h4[32 * MAX_ALPHA + p * 32 + t] = (int8_t)((v4 - lo) / 128);
+            }
             hs[p * a + t] = v;
         }
+    ctx->wide = wide;
     SA_TRY(ctx->dS4.reserve(sizeof h4), SA_ERR_MEMORY);
     SA_TRY(ctx->dS.reserve(sizeof hs), SA_ERR_MEMORY);
     SA_TRY(cudaMemcpyAsync(ctx->dS4.p, h4, sizeof h4, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
@@ -542,6 +565,11 @@ const void *long_kernel_fn(bool local, bool linked)
     return local ? (const void *)long_fill_kernel<R, true, LONG_WARPS, false>
                  : linked ? (const void *)long_fill_kernel<R, false, LONG_WARPS, true> : (const void *)long_fill_kernel<R, false, LONG_WARPS, false>;
 }
+constexpr int WIDE_R = 8;         // the wide-score variant exists for one strip height
+const void *long_kernel_wide_fn(bool local)
+{
+    return local ? (const void *)long_fill_kernel<WIDE_R, true, LONG_WARPS, false, true> : (const void *)long_fill_kernel<WIDE_R, false, LONG_WARPS, false, true>;
+}
 template <int R>
 cudaError_t launch_long_t(const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
 {
@@ -569,13 +597,27 @@ int occupancy_long_t(bool local, size_t smem, bool linked)
     case 12: return FN<12>(__VA_ARGS__);             \
     case 16: return FN<16>(__VA_ARGS__);             \
     }
-cudaError_t launch_long(int R, const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_long(int R, const LongArgs &A, bool local, int grid, size_t smem, cudaStream_t st, bool wide = false)
 {
+    if (wide) {
+        void *args[] = {(void *)&A};
+        const void *fn = long_kernel_wide_fn(local);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LONG_WARPS * 32), args, smem, st);
+    }
     LONG_DISPATCH(launch_long_t, A, local, grid, smem, st);
     return cudaErrorInvalidValue;
 }
-int occupancy_long(int R, bool local, size_t smem, bool linked = false)
+int occupancy_long(int R, bool local, size_t smem, bool linked = false, bool wide = false)
 {
+    if (wide) {
+        int nb = 0;
+        const void *fn = long_kernel_wide_fn(local);
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, LONG_WARPS * 32, smem);
+        return nb;
+    }
     LONG_DISPATCH(occupancy_long_t, local, smem, linked);
     return 0;
 }
@@ -586,9 +628,18 @@ struct LongPlan {
     size_t strip_stride, row_stride, smem;
 };
 
+// The kernels carry 4*H in 32 bits: every value the recurrence can produce must fit.  |H| <= max(|S|, gap) * (n + m).
+bool fits_s32(const sa_scoring *sc, uint64_t n, uint64_t m)
+{
+    long long big = sc->gap;
+    for (int i = 0; i < sc->alphabet_size * sc->alphabet_size; ++i) big = std::max<long long>(big, std::llabs((long long)sc->score_matrix[i]));
+    return (long double)big * (long double)(n + m + 2) * SCALE < 2147483000.0L;
+}
+
 int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P, bool traceback = true)
 {
     const bool local = sc->mode == SA_LOCAL;
+    if (!fits_s32(sc, n, m)) return SA_ERR_SCORE_RANGE;
     // Strip height, measured on B200 (tools/probe_r.py, bench.py --workload c1..c3, bench_c5.py).  Fill alone:
     // R = 8 is fastest from 4 k to 300 k rows (a step costs ~55 ns + 5 ns per row of the lane, the chain lag per
     // strip is ~80 steps); beyond that the tallest strips win because every strip stays resident in one or two
@@ -602,10 +653,13 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
         const int r = std::atoi(e);
         for (int k : kLongR) if (k == r) R = r;
     }
+    const bool wide = ctx->wide;
+    if (wide) R = WIDE_R;
     P->R = R; P->CB = cb_for(R); P->NW = R * P->CB / 16;
     P->n_strips = (uint32_t)((m + 32ull * R - 1) / (32ull * R));
-    P->smem = 32 * MAX_ALPHA + (size_t)LONG_WARPS * ((size_t)sc->alphabet_size * 32 * rpad_for(R) + (local ? ((R + 3) / 4) * 32 * 16 : 0) + 64 + 2 * PB * 4);
-    int occ = occupancy_long(R, local, P->smem);
+    const size_t planes = wide ? 2 : 1;
+    P->smem = planes * 32 * MAX_ALPHA + (size_t)LONG_WARPS * (planes * (size_t)sc->alphabet_size * 32 * rpad_for(R) + (local ? ((R + 3) / 4) * 32 * 16 : 0) + 64 + 2 * PB * 4);
+    int occ = occupancy_long(R, local, P->smem, false, wide);
     if (occ < 1) return SA_ERR_LAUNCH;
     const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
     const uint64_t needBlocks = (P->n_strips + LONG_WARPS - 1) / LONG_WARPS;
@@ -721,7 +775,7 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
     SA_TRY(cudaMemsetAsync(A.gmax, 0, 4, st), SA_ERR_LAUNCH);
     cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
-    SA_TRY(launch_long(P.R, A, local, P.grid, P.smem, st), SA_ERR_LAUNCH);
+    SA_TRY(launch_long(P.R, A, local, P.grid, P.smem, st, ctx->wide), SA_ERR_LAUNCH);
     cudaEventRecord(e1, st);
     cudaEventRecord(e2, st);
     ctx->timing.kernel_launches++;
@@ -919,7 +973,7 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
 
     sa_result hres{};
     uint64_t hoff = 0, hargmax = 0;
-    if (use_batch_path(n, m)) {
+    if (use_batch_path(n, m) && !ctx->wide) {
         // a one-pair batch through the batch kernels
         SA_TRY(ctx->misc.reserve(256), SA_ERR_MEMORY);
         int64_t hoffs[4] = {0, (int64_t)n, 0, (int64_t)m};
@@ -996,7 +1050,7 @@ int sa_fill_only(sa_context *ctx, const sa_scoring *sc, const uint8_t *text, uin
     const uint64_t cap = n + m;
     std::vector<char> t, p;
     char *pt = nullptr, *pp = nullptr;
-    if (use_batch_path(n, m)) { t.resize(cap); p.resize(cap); pt = t.data(); pp = p.data(); }
+    if (use_batch_path(n, m) && !scoring_is_wide(sc)) { t.resize(cap); p.resize(cap); pt = t.data(); pp = p.data(); }
     int rc = align_single(ctx, sc, text, n, pattern, m, &r, pt, pp, cap, pt != nullptr, argmax);
     if (rc) return rc;
     if (score) *score = r.score;
@@ -1035,6 +1089,7 @@ int sa_strip_begin(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text,
 {
     if (!ctx || !sc || !d_text || !d_pattern || n == 0 || m == 0) return SA_ERR_ARGUMENT;
     if (sc->mode != SA_GLOBAL) return SA_ERR_ARGUMENT;              // the arg-max of a local alignment is not sliced (yet)
+    if (scoring_is_wide(sc)) return SA_ERR_SCORE_RANGE;
     if (col0 + n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64 || text_total < col0 + n) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1259,6 +1314,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     if (b->n_pairs >= (1ull << 31)) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;   // as given; NULL is the CUDA default stream
+    if (scoring_is_wide(sc)) return SA_ERR_SCORE_RANGE;      // wide matrices only through the single-pair kernels (host entry points)
     int rc = upload_scoring(ctx, sc, st);
     if (rc) return rc;
     BatchClassTable T;
@@ -1312,7 +1368,8 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
     const int64_t *to = b->text_off, *po = b->pattern_off;
     if ((uint64_t)(to[N] - to[0] + po[N] - po[0]) > out->arena_capacity) return SA_ERR_CAPACITY;
 
-    // pairs too long for the batch kernels are aligned one by one through sa_align
+    // pairs too long for the batch kernels (all of them with a wide score matrix) are aligned one by one through sa_align
+    const bool wideScores = scoring_is_wide(sc);
     uint32_t max_n = 0, max_m = 0;
     uint64_t cells = 0;
     std::vector<uint64_t> longPairs;
@@ -1320,7 +1377,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         const uint64_t n = (uint64_t)(to[p + 1] - to[p]), m = (uint64_t)(po[p + 1] - po[p]);
         if (n == 0 || m == 0) return SA_ERR_ARGUMENT;
         cells += (n + 1) * (m + 1);
-        if (!batch_eligible(n, m)) { longPairs.push_back(p); continue; }
+        if (wideScores || !batch_eligible(n, m)) { longPairs.push_back(p); continue; }
         max_n = std::max<uint32_t>(max_n, (uint32_t)n);
         max_m = std::max<uint32_t>(max_m, (uint32_t)m);
     }

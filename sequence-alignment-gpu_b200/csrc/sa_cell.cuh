@@ -129,6 +129,48 @@ __device__ __forceinline__ void sweep_column(int (&c)[R], int top, int diag, con
     }
 }
 
+// Wide scores (|4*S| > 127): the profile has a second byte plane, 4*S = 128*hi + lo with lo in 0..127 and hi a signed
+// byte (|S| <= 4064); the cell adds them with two dot products -- the second one multiplies by an UNSIGNED 128, which
+// only the mixed-sign PTX form of dp4a offers.  One more FMA-pipe instruction per cell, otherwise the same cell.
+__device__ __forceinline__ int dp4a_s8_u8(const uint32_t a, const uint32_t b, const int c)
+{
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <int R, bool LOCAL, int NACC>
+__device__ __forceinline__ void sweep_column_wide(int (&c)[R], int top, int diag, const uint32_t (&prof)[(R + 3) / 4],
+                                                  const uint32_t (&profH)[(R + 3) / 4], const int KL, const int KT,
+                                                  uint32_t (&acc)[NACC], const int BITBASE, int (&bmax)[nblk_for(R)])
+{
+    int t = top, d = diag;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int x = dp4a_s8_u8(profH[r >> 2], 128u << (8 * (r & 3)), __dp4a((int)prof[r >> 2], onehot(r), d));
+        const int m = viaddmax(c[r], KL, x);
+        const int h = LOCAL ? viaddmax_relu(t, KT, m) : viaddmax(t, KT, m);
+        const int cn = h & ~3;
+        const int bit = BITBASE + 2 * r;
+        deposit_tag(acc[bit >> 5], h, cn, bit & 31);
+        d = c[r];
+        t = cn;
+        c[r] = cn;
+    }
+    if (LOCAL) {
+#pragma unroll
+        for (int b = 0; b < nblk_for(R); ++b) {
+            int v = c[b * RB];
+#pragma unroll
+            for (int q = 1; q < RB; q += 2) {
+                const int r1 = b * RB + q, r2 = b * RB + q + 1;
+                if (r2 < R && q + 1 < RB) v = __vimax3_s32(v, c[r1], c[r2]);
+                else if (r1 < R) v = max(v, c[r1]);
+            }
+            bmax[b] = v;
+        }
+    }
+}
+
 // SW arg-max tracking (row-major-first maximum, alignSequenceCPU.cpp:191-192), per lane:
 //   fast path  : colmax = max over the lane's rows (free max3 tree) and one compare per column;
 //   new record : (colmax > bestv) the lane only SNAPSHOTS its R column values into shared memory

@@ -77,7 +77,9 @@ constexpr int PB = 8;   // boundary-row prefetch block (columns)
 
 // LINKED: the variant with the cross-GPU border hand-off and the per-strip timestamps compiled in (kept out of the
 // plain kernel: even outside the step loop the extra code costs it ~5 % through register allocation).
-template <int R, bool LOCAL, int WARPS, bool LINKED = false>
+// WIDE: two profile planes for score matrices beyond +-31 (sweep_column_wide); A.S4 then holds the low plane followed
+// by the high plane (32*MAX_ALPHA bytes each).
+template <int R, bool LOCAL, int WARPS, bool LINKED = false, bool WIDE = false>
 __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
@@ -94,11 +96,13 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
     int8_t *S4s = reinterpret_cast<int8_t *>(smem);
     constexpr uint32_t snapBytes = LOCAL ? ((R + 3) / 4) * 32 * 16 : 0;
     constexpr uint32_t winBytes = 64 + 2 * PB * 4;                     // text window + top-row window
-    unsigned char *profS = smem + 32 * MAX_ALPHA + (size_t)warp * (alpha * PS + snapBytes + winBytes);
-    uint4 *snap = reinterpret_cast<uint4 *>(profS + alpha * PS);
-    unsigned char *textWin = profS + alpha * PS + snapBytes;
+    constexpr int PLANES = WIDE ? 2 : 1;
+    unsigned char *profS = smem + PLANES * 32 * MAX_ALPHA + (size_t)warp * (PLANES * alpha * PS + snapBytes + winBytes);
+    unsigned char *profHS = profS + alpha * PS;                      // WIDE: the high plane of the profile
+    uint4 *snap = reinterpret_cast<uint4 *>(profS + PLANES * alpha * PS);
+    unsigned char *textWin = profS + PLANES * alpha * PS + snapBytes;
     int *topWin = reinterpret_cast<int *>(textWin + 64);
-    for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
+    for (int i = threadIdx.x; i < PLANES * 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
     __syncthreads();
 
     const int KL = 2 - SCALE * A.gap, KT = 1 - SCALE * A.gap;
@@ -116,8 +120,10 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             if (gi < m) {
                 const int8_t *srow = S4s + 32 * min((int)A.pattern[gi], alpha - 1);
                 for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)srow[a];
+                if (WIDE) for (int a = 0; a < alpha; ++a) profHS[a * PS + off] = (unsigned char)srow[32 * MAX_ALPHA + a];
             } else {
-                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)0x80;
+                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = WIDE ? (unsigned char)0 : (unsigned char)0x80;
+                if (WIDE) for (int a = 0; a < alpha; ++a) profHS[a * PS + off] = (unsigned char)0x80;
             }
         }
         __syncwarp();
@@ -221,10 +227,13 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
         if (hasUp && lane < n) nextEnt = ld_volatile_u64(rowIn + lane);      // blocks 0..3
         take_top_block(0);
         __syncwarp();
-        uint32_t profN[NPW];
+        uint32_t profN[NPW], profHN[NPW];
 #pragma unroll
-        for (int q = 0; q < NPW; ++q) profN[q] = 0;
-        if (lane == 0 && n > 0) load_profile_words<R>(profS + (int)textWin[0] * PS, profN);
+        for (int q = 0; q < NPW; ++q) { profN[q] = 0; profHN[q] = 0; }
+        if (lane == 0 && n > 0) {
+            load_profile_words<R>(profS + (int)textWin[0] * PS, profN);
+            if (WIDE) load_profile_words<R>(profHS + (int)textWin[0] * PS, profHN);
+        }
         int topN = topWin[0];
         uint32_t acc[NW];
 #pragma unroll
@@ -237,9 +246,9 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             constexpr int MODE = decltype(modeTag)::value;
             constexpr bool FAST = MODE != 0;
             const int jt = k - lane, k1 = k + 1, jn = k1 - lane;
-            uint32_t prof[NPW];
+            uint32_t prof[NPW], profH[NPW];
 #pragma unroll
-            for (int q = 0; q < NPW; ++q) prof[q] = profN[q];
+            for (int q = 0; q < NPW; ++q) { prof[q] = profN[q]; profH[q] = profHN[q]; }
             const int topv = topN;
             if (!FAST) upkeep(k1);
             // next step's letter first: its shared-memory latency hides behind the sweep below
@@ -251,7 +260,8 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
             int bmax[nblk_for(R)];
             if (active) {
                 const int top = (lane == 0) ? topv : up;
-                sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
+                if (WIDE) sweep_column_wide<R, LOCAL, NW>(c, top, prevTop, prof, profH, KL, KT, acc, 2 * R * kk, bmax);
+                else sweep_column<R, LOCAL, NW>(c, top, prevTop, prof, KL, KT, acc, 2 * R * kk, bmax);
                 prevTop = top;
                 bottom = c[R - 1];
             }
@@ -270,7 +280,10 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
                     }
                 }
             }
-            if (nextActive) load_profile_words<R>(profS + letterN * PS + lane * RPAD, profN);
+            if (nextActive) {
+                load_profile_words<R>(profS + letterN * PS + lane * RPAD, profN);
+                if (WIDE) load_profile_words<R>(profHS + letterN * PS + lane * RPAD, profHN);
+            }
             if (kk == CB - 1) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w) { dbase[(size_t)((k / CB) * NW + w) * 32] = acc[w]; acc[w] = 0; }

@@ -119,8 +119,8 @@ def test_argument_errors(sa, aligner):
     mat = helpers.matrices()["dna/blast.txt"]
     with pytest.raises(sa.SaError):
         aligner.align(0, 4, mat, 5, np.zeros(0, np.uint8), np.zeros(3, np.uint8))
-    with pytest.raises(sa.SaError):
-        aligner.align(0, 4, np.full(16, 1000, np.int32), 5, np.zeros(3, np.uint8), np.zeros(3, np.uint8))
+    with pytest.raises(sa.SaError):      # beyond the two-plane profile (|S| <= 4064); 1000 is fine, see test_wide_score_matrices
+        aligner.align(0, 4, np.full(16, 5000, np.int32), 5, np.zeros(3, np.uint8), np.zeros(3, np.uint8))
 
 
 def test_host_batch_vs_oracle(sa, aligner, oracle):
@@ -412,3 +412,34 @@ def test_gap_penalty_extremes(sa, aligner, oracle, force_path, gap):
         for i in range(0, 300, 7):
             want = oracle.align(mode, 23, b62, gap, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]])
             assert_same(sa.unpack_batch(out, i), want, ("batch", mode, gap, i))
+
+
+def test_wide_score_matrices(sa, aligner, oracle):
+    """Score matrices beyond +-31 (the reference takes any int): they run through the long-pair kernel with the
+    two-plane profile, whatever the pair size -- single pairs, a host batch; the device-resident batch refuses them."""
+    rng = np.random.default_rng(4064)
+    big_dna = np.full((4, 4), -77, np.int32); np.fill_diagonal(big_dna, 100)
+    b62x25 = helpers.matrices()["protein/blosum62.txt"].astype(np.int32) * 25
+    edge = rng.integers(-4064, 4065, (23, 23)).astype(np.int32); edge[0, 0] = 4064; edge[1, 2] = -4064
+    for alpha, mat, gap in ((4, big_dna, 60), (23, b62x25, 125), (23, edge, 900), (4, big_dna, 5)):
+        for mode in (0, 1):
+            for n in (7, 300, 2100):
+                t, p = helpers.random_case(rng, alpha, n)
+                assert_same(aligner.align(mode, alpha, mat, gap, t, p), oracle.align(mode, alpha, mat, gap, t, p), ("wide", alpha, gap, mode, n))
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(24, seed=9, lo=60, hi=200)
+    out = aligner.align_batch(1, 23, b62x25, 125, T, toff, P, poff)
+    for i in range(24):
+        assert_same(sa.unpack_batch(out, i), oracle.align(1, 23, b62x25, 125, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]), ("wide batch", i))
+    too_big = big_dna.copy(); too_big[0, 0] = 5000
+    with pytest.raises(sa.SaError) as e:
+        aligner.align(0, 4, too_big, 5, T[:50] % 4, P[:40] % 4)
+    assert e.value.status == -5
+    # 4*H must fit 32 bits: a gap of 2^20 on a 600-residue pair would not -- refused loudly, not wrapped
+    with pytest.raises(sa.SaError) as e:
+        aligner.align(0, 4, big_dna, 1 << 20, T[:600] % 4, P[:580] % 4)
+    assert e.value.status == -5
+    # after a wide call the context must be back on the fast paths
+    t, p = helpers.random_case(rng, 4, 200)
+    blast = helpers.matrices()["dna/blast.txt"]
+    assert_same(aligner.align(0, 4, blast, 5, t, p), oracle.align(0, 4, blast, 5, t, p), "narrow after wide")

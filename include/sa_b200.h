@@ -82,7 +82,9 @@ typedef struct sa_context sa_context;
 /* Number of usable CUDA devices (0 when none). */
 int sa_device_count(void);
 
-/* Creates a context bound to `device` (the reference hard-codes device 0,
+/* A context is NOT thread-safe: it owns streams, events and growing workspaces that its calls reuse.  Use one
+ * context per host thread (several contexts on one device are fine; the tests run up to eight).
+ * Creates a context bound to `device` (the reference hard-codes device 0,
  * alignSequenceGPU.cu:476).  Owns a stream, pinned staging and a growing
  * device workspace, so repeated calls do not pay cudaMalloc/cudaMallocHost per
  * call like initMemory does (alignSequenceGPU.cu:362-461). */

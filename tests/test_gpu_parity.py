@@ -443,3 +443,23 @@ def test_wide_score_matrices(sa, aligner, oracle):
     t, p = helpers.random_case(rng, 4, 200)
     blast = helpers.matrices()["dna/blast.txt"]
     assert_same(aligner.align(0, 4, blast, 5, t, p), oracle.align(0, 4, blast, 5, t, p), "narrow after wide")
+
+
+def test_batch_length_spectrum(sa, aligner, oracle):
+    """One host batch spanning everything the batch kernels take -- texts 1..4096, patterns 1..1536, tiny and ragged
+    pairs, similar and unrelated ones (every class, lanes without rows, pattern > text) -- against the oracle."""
+    rng = np.random.default_rng(2025)
+    b50 = helpers.matrices()["protein/blosum50.txt"]
+    N = 360
+    for mode in (0, 1):
+        n = np.concatenate((rng.integers(1, 40, 80), rng.integers(1, 700, 200), rng.integers(700, 4097, 80)))
+        m = np.concatenate((rng.integers(1, 40, 80), rng.integers(1, 400, 200), rng.integers(300, 1537, 80)))
+        rng.shuffle(n); rng.shuffle(m)
+        toff = np.concatenate(([0], np.cumsum(n))).astype(np.int64); poff = np.concatenate(([0], np.cumsum(m))).astype(np.int64)
+        T = rng.integers(0, 23, toff[-1], dtype=np.uint8); P = rng.integers(0, 23, poff[-1], dtype=np.uint8)
+        for i in range(0, N, 3):
+            k = min(n[i], m[i]); P[poff[i]:poff[i] + k] = T[toff[i]:toff[i] + k]
+        out = aligner.align_batch(mode, 23, b50, 4, T, toff, P, poff)
+        for i in range(N):
+            assert_same(sa.unpack_batch(out, i), oracle.align(mode, 23, b50, 4, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]),
+                        ("spectrum", mode, i, int(n[i]), int(m[i])))

@@ -111,6 +111,13 @@ def batch(al, sa, nb, rng):
     for t, p in reqs:
         al.align(0, 23, mat, 5, t, p)
     print(f"GPU = {(time.perf_counter() - t0) * 1e3:.1f} ms")
+    # the same requests as ONE sa_align_batch call: the dispatcher runs several such pairs side by side
+    T = np.concatenate([t for t, _ in reqs]); P = np.concatenate([p for _, p in reqs])
+    toff = np.arange(nb + 1, dtype=np.int64) * (cols - 1); poff = np.arange(nb + 1, dtype=np.int64) * (rows - 1)
+    al.align_batch(0, 23, mat, 5, T, toff, P, poff)
+    t0 = time.perf_counter()
+    al.align_batch(0, 23, mat, 5, T, toff, P, poff)
+    print(f"GPU, one sa_align_batch call = {(time.perf_counter() - t0) * 1e3:.1f} ms")
 
 
 def maxlength(al, mode, rng, sizes):

@@ -14,6 +14,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace sa;
@@ -89,6 +93,9 @@ struct sa_context {
     Slot slot[NSLOT];
     uint32_t epoch = 0;
     bool wide = false;                      // the scoring uploaded last needs the two-plane profile
+    // sub-contexts for the long members of a host batch: several medium-size pairs run side by side (each is a
+    // small cooperative launch), one host thread per sub-context
+    std::vector<sa_context *> workers;
     size_t rowbuf_entries_valid = 0;
     // column-slice state of sa_strip_fill, consumed by sa_strip_traceback
     struct StripState {
@@ -894,6 +901,8 @@ int sa_create(int device, sa_context **out)
 void sa_destroy(sa_context *ctx)
 {
     if (!ctx) return;
+    for (sa_context *w : ctx->workers) sa_destroy(w);
+    ctx->workers.clear();
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf, &ctx->tbbuf, &ctx->snapbuf})
@@ -1450,17 +1459,65 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         const uint64_t base0 = (uint64_t)(to[0] + po[0]);
         if (base0) for (uint64_t p = 0; p < N; ++p) out->aln_off[p] -= base0;
     }
-    for (uint64_t p : longPairs) {
+    // Long members: one by one through sa_align -- but several at a time when there are several: a pair of a few
+    // thousand residues fills a fraction of the GPU (its cooperative launch has a handful of blocks), so up to
+    // SA_LONG_WORKERS (default 8, memory permitting) sub-contexts run them side by side, one host thread each.
+    auto align_member = [&](sa_context *c, uint64_t p, sa_timing *k) -> int {
         const uint64_t n = (uint64_t)(to[p + 1] - to[p]), m = (uint64_t)(po[p + 1] - po[p]);
         const uint64_t slot = (uint64_t)(to[p] - to[0]) + (uint64_t)(po[p] - po[0]);
-        rc = sa_align(ctx, sc, b->text + to[p], n, b->pattern + po[p], m, &out->results[p],
-                      out->aligned_text + slot, out->aligned_pattern + slot, n + m);
-        if (rc) return rc;
+        const int r = sa_align(c, sc, b->text + to[p], n, b->pattern + po[p], m, &out->results[p],
+                               out->aligned_text + slot, out->aligned_pattern + slot, n + m);
+        if (r) return r;
         out->aln_off[p] = slot;
-        sa_timing k{};
-        sa_last_timing(ctx, &k);
-        tm.total_us += k.total_us; tm.fill_us += k.fill_us; tm.traceback_us += k.traceback_us;
-        tm.kernel_launches += k.kernel_launches;
+        sa_last_timing(c, k);
+        return SA_OK;
+    };
+    size_t nWorkers = 1;
+    if (longPairs.size() >= 2) {
+        nWorkers = 8;
+        if (const char *e = std::getenv("SA_LONG_WORKERS")) nWorkers = (size_t)std::max(1, std::atoi(e));
+        uint64_t worst = 0;                                     // direction bytes of the largest member
+        for (uint64_t p : longPairs) worst = std::max<uint64_t>(worst, (uint64_t)(to[p + 1] - to[p] + 64) * (uint64_t)(po[p + 1] - po[p] + 512) / 4);
+        size_t freeB = 0, totalB = 0;
+        cudaMemGetInfo(&freeB, &totalB);
+        nWorkers = std::min<size_t>({nWorkers, longPairs.size(), std::max<size_t>(1, (size_t)(0.6 * (double)freeB / (double)(worst + (64u << 20))))});
+    }
+    if (nWorkers <= 1) {
+        for (uint64_t p : longPairs) {
+            sa_timing k{};
+            rc = align_member(ctx, p, &k);
+            if (rc) return rc;
+            tm.total_us += k.total_us; tm.fill_us += k.fill_us; tm.traceback_us += k.traceback_us;
+            tm.kernel_launches += k.kernel_launches;
+        }
+    } else {
+        while (ctx->workers.size() < nWorkers) {
+            sa_context *w = nullptr;
+            if (sa_create(ctx->device, &w) != SA_OK) break;
+            ctx->workers.push_back(w);
+        }
+        nWorkers = std::min(nWorkers, ctx->workers.size());
+        if (nWorkers == 0) return SA_ERR_MEMORY;
+        std::atomic<size_t> next(0);
+        std::atomic<int> firstErr(0);
+        std::mutex mu;
+        const auto t0 = std::chrono::steady_clock::now();
+        auto work = [&](size_t w) {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= longPairs.size() || firstErr.load()) break;
+                sa_timing k{};
+                const int r = align_member(ctx->workers[w], longPairs[i], &k);
+                if (r) { int z = 0; firstErr.compare_exchange_strong(z, r); break; }
+                std::lock_guard<std::mutex> g(mu);
+                tm.fill_us += k.fill_us; tm.traceback_us += k.traceback_us; tm.kernel_launches += k.kernel_launches;
+            }
+        };
+        std::vector<std::thread> th;
+        for (size_t w = 0; w < nWorkers; ++w) th.emplace_back(work, w);
+        for (auto &t : th) t.join();
+        if (firstErr.load()) return firstErr.load();
+        tm.total_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     }
     ctx->timing = tm;
     ctx->timing_dirty = false;

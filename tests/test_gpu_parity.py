@@ -463,3 +463,20 @@ def test_batch_length_spectrum(sa, aligner, oracle):
         for i in range(N):
             assert_same(sa.unpack_batch(out, i), oracle.align(mode, 23, b50, 4, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]),
                         ("spectrum", mode, i, int(n[i]), int(m[i])))
+
+
+def test_host_batch_of_medium_pairs_runs_concurrently(sa, aligner, oracle):
+    """A host batch whose members are all too long for the batch kernels: they go through the long-pair kernels on
+    several worker sub-contexts side by side (SA_LONG_WORKERS); every Response must still equal the oracle's."""
+    rng = np.random.default_rng(8192)
+    blast = helpers.matrices()["dna/blast.txt"]
+    n = rng.integers(1700, 5200, 14); m = rng.integers(1600, 4800, 14)
+    toff = np.concatenate(([0], np.cumsum(n))).astype(np.int64); poff = np.concatenate(([0], np.cumsum(m))).astype(np.int64)
+    T = rng.integers(0, 4, toff[-1], dtype=np.uint8); P = rng.integers(0, 4, poff[-1], dtype=np.uint8)
+    for i in range(0, 14, 2):
+        k = min(n[i], m[i]); P[poff[i]:poff[i] + k] = T[toff[i]:toff[i] + k]; P[poff[i]:poff[i] + k:11] ^= 1
+    for mode in (0, 1):
+        out = aligner.align_batch(mode, 4, blast, 5, T, toff, P, poff)
+        for i in range(14):
+            assert_same(sa.unpack_batch(out, i), oracle.align(mode, 4, blast, 5, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]),
+                        ("medium batch", mode, i))

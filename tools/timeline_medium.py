@@ -16,6 +16,6 @@ for _ in range(2): al.align_batch(0, 23, mat, 5, T, toff, P, poff)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     al.align_batch(0, 23, mat, 5, T, toff, P, poff)
     torch.cuda.synchronize()
-ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "long_fill" in e.name], key=lambda e: e.time_range.start)
+ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
 t0 = ev[0].time_range.start
 for e in ev: print(f"{(e.time_range.start - t0) / 1e3:8.3f} ms +{(e.time_range.end - e.time_range.start) / 1e3:7.3f} ms {e.name[:40]}")

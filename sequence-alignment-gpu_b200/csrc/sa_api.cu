@@ -695,15 +695,18 @@ int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, u
         T.S = ctx->dS.as<int32_t>(); T.alpha = alpha; T.gap = gap; T.local = local;
         T.n_strips = P.n_strips;
         T.start_given = start_row >= 0 ? 1 : 0; T.start_row = (int)std::max<long long>(0, start_row); T.slice = slice ? 1 : 0;
-        int Wd = 16;
-        while (Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;          // power of two <= ROWS/2
+        // band of candidates around the predicted crossing: +-max(512 columns, n/50).  (A crossing outside the band
+        // only costs a serial segment; a wide band costs walkers far from the path, whose own paths run long gap
+        // stretches: +-2048 made the walkers 0.47 ms of a 1.3 ms call at 3.9 k x 3.7 k.)
+        const uint64_t half = std::max<uint64_t>(512, n / 50);
+        // candidate spacing: as fine as 8 columns -- two candidates 8 apart merge within a strip far more often than
+        // two that are 64 apart (unrelated 32 k x 32 k sequences: traceback 6.5 -> 0.8 ms) -- but at most ~1000
+        // candidates per line, and never more than half a strip height
+        int Wd = 8;
+        while ((uint64_t)Wd * 500 < half && Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;
         if (const char *e = std::getenv("SA_TB_WD")) { const int w = std::atoi(e); if (w >= 1) Wd = w; }
         T.Wd = Wd; T.Q = (int)((n + Wd - 1) / Wd);
         {
-            // band of candidates around the predicted crossing: +-max(512 columns, n/50).  (A crossing outside the
-            // band only costs a serial segment; a wide band costs walkers far from the path, whose own paths run long
-            // gap stretches: +-2048 made the walkers 0.47 ms of a 1.3 ms call at 3.9 k x 3.7 k.)
-            const uint64_t half = std::max<uint64_t>(512, n / 50);
             int bq = (int)((half + Wd - 1) / Wd);
             if (const char *e = std::getenv("SA_TB_BAND")) { const int b = std::atoi(e); if (b >= 1) bq = b; }
             T.BQ = std::max(1, std::min(bq, std::max(1, T.Q / 2)));

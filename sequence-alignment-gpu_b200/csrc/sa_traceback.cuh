@@ -149,7 +149,11 @@ __global__ void tb_prepare_kernel(const TbArgs A)
 // crossing (start cell, slope); a crossing outside the band only costs a serial fallback segment.
 __device__ __forceinline__ int tb_band_q0(const TbArgs &A, const int s)
 {
-    const double pred = (double)A.st->j0 - (double)(A.st->i0 - s * A.Lay.ROWS) * A.slope;
+    // local alignments: the slope of the line from the end cell to the origin (clamped) -- exact for an alignment that
+    // spans the matrix, harmless for a short one; with slope 1 a 100 k local alignment drifted 5 k columns out of
+    // the band and was walked serially (19.5 ms instead of 1.2)
+    const double slope = A.local ? fmin(1.25, fmax(0.8, (double)A.st->j0 / fmax(1.0, (double)A.st->i0))) : A.slope;
+    const double pred = (double)A.st->j0 - (double)(A.st->i0 - s * A.Lay.ROWS) * slope;
     const int qc = (int)(fmax(0.0, fmin(pred, (double)A.Lay.n)) / (double)A.Wd);
     return max(0, min(qc - A.BQ, A.Q - 2 * A.BQ));
 }

@@ -704,6 +704,9 @@ int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, u
         // candidates per line, and never more than half a strip height
         int Wd = 8;
         while ((uint64_t)Wd * 500 < half && Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;
+        // ... and at most ~200 k walkers per call: a 500 k-column slice of config 5 has 1857 strips, and 625 candidates
+        // on each (spacing 32) cost 17 ms per slice against 78 candidates (spacing 256), 0.325 -> 0.360 s at N = 2
+        while ((uint64_t)P.n_strips * (2 * half / Wd + 1) > 200000 && Wd * 2 <= 16 * P.R && Wd < 256) Wd *= 2;
         if (const char *e = std::getenv("SA_TB_WD")) { const int w = std::atoi(e); if (w >= 1) Wd = w; }
         T.Wd = Wd; T.Q = (int)((n + Wd - 1) / Wd);
         {

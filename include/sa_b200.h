@@ -73,6 +73,8 @@ typedef struct {
     double total_us;      /* first event to last event */
     uint64_t cells;       /* sum over pairs of (pattern_len+1)*(text_len+1) (tests/benchmarks.cu:85) */
     uint32_t kernel_launches;
+    uint64_t h2d_bytes;   /* sa_align_batch: bytes copied host->device ... */
+    uint64_t d2h_bytes;   /* ... and device->host by the last call (0 from the other entry points) */
 } sa_timing;
 
 typedef struct sa_context sa_context;

@@ -71,7 +71,7 @@ class _Result(C.Structure):
 class _Timing(C.Structure):
     _fields_ = [("h2d_us", C.c_double), ("fill_us", C.c_double), ("traceback_us", C.c_double),
                 ("d2h_us", C.c_double), ("total_us", C.c_double), ("cells", C.c_uint64),
-                ("kernel_launches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class _Batch(C.Structure):

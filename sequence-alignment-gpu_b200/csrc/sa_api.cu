@@ -65,7 +65,10 @@ constexpr int NSLOT = 3;   // pipeline depth of the host batch path
 struct Slot {              // per-chunk device buffers of the host batch path
     cudaStream_t stream = nullptr;
     DevBuf text, pattern, toff, poff, results, alnoff, outT, outP, dirs, fill, order, snap;
+    DevBuf packT, packP, noff;             // staged host path: packed strings of the chunk
+    cudaEvent_t packed = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t in = nullptr, out = nullptr;      // staged host path: inputs landed / outputs drained
 };
 
 } // namespace
@@ -82,6 +85,7 @@ struct sa_context {
     DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf, tbbuf, snapbuf;
     // device-batch pipeline: fills on the caller's stream, tracebacks on `stream`, two buffer sets
     DevBuf pdirs[2], psort[2];
+    DevBuf packstate;                     // staged host path: running total of the packed strings
     cudaEvent_t evFill[2] = {}, evTrace[2] = {};
     // the class kernels of one chunk are independent: they run on side streams so that the tail of
     // one class overlaps the body of the next
@@ -430,6 +434,97 @@ int occupancy_batch(const BatchCfg &cfg, bool local, size_t smem)
     SA_BATCH_CFG_LIST(X)
 #undef X
     return 0;
+}
+
+// ---- staged host path: strings of a chunk packed back to back before they cross PCIe ----
+// The traceback writes pair p's strings at the END of its slot of text_len + pattern_len bytes (it walks backwards and
+// does not know the length in advance), so a chunk's arenas are about half slack.  These kernels pack the used
+// parts; aln_off is rewritten to the packed position (absolute over the whole call: `running` carries the total of the
+// earlier chunks), and the chunk's packed size is stored straight into pinned host memory for the host's copy call.
+struct CompactArgs {
+    const sa_result *results; uint64_t *aln_off; uint32_t count;
+    const char *srcT, *srcP;              // arenas as the traceback addressed them (aln_off-based)
+    char *dstT, *dstP;                    // packed chunk buffers
+    unsigned long long *noff;             // count entries: packed offsets inside the pair's block of 1024 pairs
+    unsigned long long *block_base;       // per block of 1024 pairs: absolute packed offset; one more entry: the chunk's
+    unsigned long long *running;          // device: total of the chunks before this one
+    volatile unsigned long long *host_total;     // pinned host: this chunk's packed bytes
+};
+
+// All three kernels use 128-thread blocks without shared-memory demands worth mentioning, so that -- like the traceback
+// blocks -- they find room on SMs that the fill blocks of the following chunk already occupy (a 1024-thread scan block
+// had to wait for an SM to drain, which held up the traceback stream: 33.8 -> 36.5 ms per 1 M pairs).
+constexpr int PACK_ITEMS = 8, PACK_BLOCK = 128 * PACK_ITEMS;      // pairs per block of the local scan
+
+__device__ __forceinline__ unsigned long long pack_block_exscan(unsigned long long v, unsigned long long *total)
+{
+    __shared__ unsigned long long wsum[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    unsigned long long before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (k < w) before += wsum[k]; all += wsum[k]; }
+    *total = all;
+    __syncthreads();
+    return before + inc - v;
+}
+
+// (1) per block of 1024 pairs: offsets inside the block, and the block's total
+__global__ void __launch_bounds__(128) pack_local_kernel(const CompactArgs A)
+{
+    const uint32_t b0 = blockIdx.x * PACK_BLOCK + threadIdx.x * PACK_ITEMS;
+    unsigned long long len[PACK_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < PACK_ITEMS; ++k) { len[k] = b0 + k < A.count ? A.results[b0 + k].aln_len : 0ull; s += len[k]; }
+    unsigned long long total;
+    unsigned long long off = pack_block_exscan(s, &total);
+#pragma unroll
+    for (int k = 0; k < PACK_ITEMS; ++k) { if (b0 + k < A.count) A.noff[b0 + k] = off; off += len[k]; }
+    if (threadIdx.x == 0) A.block_base[blockIdx.x] = total;
+}
+
+// (2) one block: block totals -> absolute bases (after the chunks before this one); chunk total to the host
+__global__ void __launch_bounds__(128) pack_bases_kernel(const CompactArgs A)
+{
+    const uint32_t nb = (A.count + PACK_BLOCK - 1) / PACK_BLOCK;
+    const unsigned long long start = *A.running;
+    unsigned long long carry = start;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 128) {
+        const uint32_t i = b0 + threadIdx.x;
+        const unsigned long long v = i < nb ? A.block_base[i] : 0ull;
+        unsigned long long total;
+        const unsigned long long ex = pack_block_exscan(v, &total);
+        if (i < nb) A.block_base[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        A.block_base[nb] = start;             // the chunk's own base, for the copy kernel
+        *A.running = carry;
+        *A.host_total = carry - start;
+        __threadfence_system();
+    }
+}
+
+// (3) one warp per pair: used part of the slot -> packed position; aln_off follows
+__global__ void __launch_bounds__(128) compact_copy_kernel(const CompactArgs A)
+{
+    const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (pair >= A.count) return;
+    const uint32_t len = (uint32_t)A.results[pair].aln_len;
+    const unsigned long long dstAbs = A.block_base[pair / PACK_BLOCK] + A.noff[pair];
+    const unsigned long long base = A.block_base[(A.count + PACK_BLOCK - 1) / PACK_BLOCK];
+    const char *sT = A.srcT + A.aln_off[pair], *sP = A.srcP + A.aln_off[pair];
+    char *dT = A.dstT + (dstAbs - base), *dP = A.dstP + (dstAbs - base);
+    for (uint32_t k = lane; k < len; k += 32) { dT[k] = sT[k]; dP[k] = sP[k]; }
+    __syncwarp();
+    if (lane == 0) A.aln_off[pair] = dstAbs;
 }
 
 // Enqueue binning + fill (one launch per class) + traceback for pairs [first, first+count) of a
@@ -889,6 +984,9 @@ int sa_create(int device, sa_context **out)
     for (auto &s : ctx->slot) {
         cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.in, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.out, cudaEventDisableTiming);
     }
     if (const char *e = std::getenv("SA_DIRS_BUDGET_MB")) ctx->dirs_budget = (size_t)std::atoll(e) << 20;
     if (const char *e = std::getenv("SA_HOST_DIRS_BUDGET_MB")) ctx->host_dirs_budget = (size_t)std::atoll(e) << 20;
@@ -898,6 +996,9 @@ int sa_create(int device, sa_context **out)
     cudaFuncSetAttribute(batch_classify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(batch_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(batch_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(pack_local_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(pack_bases_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(compact_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (const char *e = std::getenv("SA_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));
     if (const char *e = std::getenv("SA_TB_BLOCKS_PER_SM")) ctx->tb_blocks_per_sm = std::max(1, std::atoi(e));
     *out = ctx;
@@ -915,9 +1016,12 @@ void sa_destroy(sa_context *ctx)
         b->release();
     ctx->pin.release();
     for (auto &s : ctx->slot) {
-        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order, &s.snap}) b->release();
+        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order, &s.snap, &s.packT, &s.packP, &s.noff}) b->release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.in) cudaEventDestroy(s.in);
+        if (s.packed) cudaEventDestroy(s.packed);
+        if (s.out) cudaEventDestroy(s.out);
     }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->evpool) if (e) cudaEventDestroy(e);
@@ -930,6 +1034,7 @@ void sa_destroy(sa_context *ctx)
     for (auto &b : ctx->clsSnap) b.release();
     for (auto &b : ctx->pdirs) b.release();
     for (auto &b : ctx->psort) b.release();
+    ctx->packstate.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1401,6 +1506,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
     reset_timing(ctx);
     sa_timing tm{};
     tm.cells = cells;
+    uint64_t d2hBytes = 0;
 
     if (max_m > 0) {
         BatchClassTable T;
@@ -1408,11 +1514,130 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         // chunk size: bounded by the direction budget and by ~1/8 of the batch for copy/compute overlap
         const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;
         uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->host_dirs_budget / NSLOT / perPair));
-        chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, (N + 7) / 8));
+        uint64_t nChunks = 8;
+        if (const char *e = std::getenv("SA_HOST_CHUNKS")) nChunks = (uint64_t)std::max(1, std::atoi(e));
+        chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, (N + nChunks - 1) / nChunks));
         cudaEventRecord(ctx->ev[0], ctx->stream);
         for (auto &s : ctx->slot) cudaStreamWaitEvent(s.stream, ctx->ev[0], 0);
+        // Staged pipeline (default; SA_HOST_PIPELINE=slots selects the older one below): the shape of the device-resident
+        // pipeline with the copies on their own streams.  All fills run on ONE stream, all tracebacks on ctx->stream
+        // (one block per SM next to the fill blocks of the following chunk), host->device copies on a third stream and
+        // device->host copies on a fourth; everything is ordered by events, the host only waits at the end.
+        const char *hp = std::getenv("SA_HOST_PIPELINE");
+        const bool staged = !(hp && std::strcmp(hp, "slots") == 0) && N >= 8192;
+        if (staged) {
+            const cudaStream_t stIn = ctx->slot[0].stream, stOut = ctx->slot[1].stream, stFill = ctx->slot[2].stream;
+            chunk = std::min<uint64_t>(chunk, N);
+            const uint64_t nc = (N + chunk - 1) / chunk;
+            chunk = (N + nc - 1) / nc;                                   // equal chunks
+            uint64_t maxT = 0, maxP = 0;
+            for (uint64_t first = 0; first < N; first += chunk) {
+                const uint64_t count = std::min<uint64_t>(chunk, N - first);
+                maxT = std::max<uint64_t>(maxT, (uint64_t)(to[first + count] - to[first]));
+                maxP = std::max<uint64_t>(maxP, (uint64_t)(po[first + count] - po[first]));
+            }
+            // buffers at their final size before anything is in flight (growing one frees it, which waits for the device)
+            for (auto &s : ctx->slot) {
+                SA_TRY(s.text.reserve(maxT + 16), SA_ERR_MEMORY);
+                SA_TRY(s.pattern.reserve(maxP + 16), SA_ERR_MEMORY);
+                SA_TRY(s.toff.reserve((chunk + 1) * 8), SA_ERR_MEMORY);
+                SA_TRY(s.poff.reserve((chunk + 1) * 8), SA_ERR_MEMORY);
+                SA_TRY(s.results.reserve(chunk * sizeof(sa_result)), SA_ERR_MEMORY);
+                SA_TRY(s.alnoff.reserve(chunk * 8), SA_ERR_MEMORY);
+                SA_TRY(s.outT.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
+                SA_TRY(s.outP.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
+                SA_TRY(s.fill.reserve(chunk * 12 + 64), SA_ERR_MEMORY);
+            }
+            for (int k = 0; k < 2; ++k) {
+                SA_TRY(ctx->pdirs[k].reserve(batch_dirs_bound(T, chunk) * 4), SA_ERR_MEMORY);
+                SA_TRY(ctx->psort[k].reserve(batch_sort_bytes(chunk)), SA_ERR_MEMORY);
+            }
+            // strings packed on the device before the copy (SA_HOST_PACK=0: whole slots as they are).  Long members write
+            // into their slots afterwards, which the packed layout would overlap: such batches stay unpacked.
+            const char *pe = std::getenv("SA_HOST_PACK");
+            const bool pack = longPairs.empty() && !(pe && pe[0] == '0');
+            if (pack) {
+                for (auto &s : ctx->slot) {
+                    SA_TRY(s.packT.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
+                    SA_TRY(s.packP.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
+                    SA_TRY(s.noff.reserve((chunk + chunk / PACK_BLOCK + 4) * 8), SA_ERR_MEMORY);
+                }
+                SA_TRY(ctx->pin.reserve(256), SA_ERR_MEMORY);
+                SA_TRY(ctx->packstate.reserve(64), SA_ERR_MEMORY);
+                SA_TRY(cudaMemsetAsync(ctx->packstate.as<unsigned long long>(), 0, 8, ctx->stream), SA_ERR_LAUNCH);   // running total
+            }
+            uint64_t hostBase = 0;
+            auto drain = [&](uint64_t k) -> int {          // device->host copies of chunk k, sized by its packed total
+                Slot &s = ctx->slot[k % NSLOT];
+                const uint64_t first = k * chunk, count = std::min<uint64_t>(chunk, N - first);
+                SA_TRY(cudaEventSynchronize(s.packed), SA_ERR_LAUNCH);
+                const uint64_t total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p)[k % NSLOT];
+                if (hostBase + total > out->arena_capacity) return SA_ERR_CAPACITY;
+                SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                if (total) {
+                    SA_TRY(cudaMemcpyAsync(out->aligned_text + hostBase, s.packT.p, total, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                    SA_TRY(cudaMemcpyAsync(out->aligned_pattern + hostBase, s.packP.p, total, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                }
+                SA_TRY(cudaEventRecord(s.out, stOut), SA_ERR_LAUNCH);
+                hostBase += total;
+                d2hBytes += count * (sizeof(sa_result) + 8) + 2 * total;
+                return SA_OK;
+            };
+            uint64_t c = 0;
+            for (uint64_t first = 0; first < N; first += chunk, ++c) {
+                Slot &s = ctx->slot[c % NSLOT];
+                const int d = (int)(c & 1);
+                const uint64_t count = std::min<uint64_t>(chunk, N - first);
+                const int64_t tb = to[first], pb = po[first];
+                const uint64_t tbytes = (uint64_t)(to[first + count] - tb), pbytes = (uint64_t)(po[first + count] - pb);
+                const uint64_t arena = tbytes + pbytes;
+                if (c >= NSLOT) cudaStreamWaitEvent(stIn, s.out, 0);          // the set's previous chunk has drained
+                SA_TRY(cudaMemcpyAsync(s.text.p, b->text + tb, tbytes, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
+                SA_TRY(cudaMemcpyAsync(s.pattern.p, b->pattern + pb, pbytes, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
+                SA_TRY(cudaMemcpyAsync(s.toff.p, to + first, (count + 1) * 8, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
+                SA_TRY(cudaMemcpyAsync(s.poff.p, po + first, (count + 1) * 8, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
+                SA_TRY(cudaEventRecord(s.in, stIn), SA_ERR_LAUNCH);
+                cudaStreamWaitEvent(stFill, s.in, 0);
+                if (c >= 2) cudaStreamWaitEvent(stFill, ctx->evTrace[d], 0);  // direction set d is free again
+                sa_batch cb{count, s.text.as<uint8_t>() - tb, s.toff.as<int64_t>(), s.pattern.as<uint8_t>() - pb, s.poff.as<int64_t>()};
+                char *oT = s.outT.as<char>() - (tb + pb), *oP = s.outP.as<char>() - (tb + pb);
+                rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
+                                   ctx->pdirs[d].as<uint32_t>(), ctx->pdirs[d].cap / 4, s.fill.p, ctx->psort[d].p, &ctx->snapbuf,
+                                   stFill, 0, (uint32_t)count, ctx->stream, ctx->evFill[d], /*tbShare=*/first + chunk < N);
+                if (rc) return rc;
+                SA_TRY(cudaEventRecord(ctx->evTrace[d], ctx->stream), SA_ERR_LAUNCH);
+                if (!pack) {
+                    cudaStreamWaitEvent(stOut, ctx->evTrace[d], 0);
+                    SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                    SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                    SA_TRY(cudaMemcpyAsync(out->aligned_text + (tb - to[0]) + (pb - po[0]), s.outT.p, arena, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                    SA_TRY(cudaMemcpyAsync(out->aligned_pattern + (tb - to[0]) + (pb - po[0]), s.outP.p, arena, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                    SA_TRY(cudaEventRecord(s.out, stOut), SA_ERR_LAUNCH);
+                    d2hBytes += count * (sizeof(sa_result) + 8) + 2 * arena;
+                    continue;
+                }
+                // pack the chunk's strings (behind its traceback, next to the following fill), then let the host -- two
+                // chunks behind the enqueue front, so that the fills never wait for it -- copy exactly the packed bytes
+                CompactArgs K{};
+                K.results = s.results.as<sa_result>(); K.aln_off = s.alnoff.as<uint64_t>(); K.count = (uint32_t)count;
+                K.srcT = oT; K.srcP = oP; K.dstT = s.packT.as<char>(); K.dstP = s.packP.as<char>();
+                K.noff = s.noff.as<unsigned long long>(); K.running = ctx->packstate.as<unsigned long long>();
+                K.host_total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p) + (c % NSLOT);
+                K.block_base = K.noff + chunk;
+                pack_local_kernel<<<(unsigned)((count + PACK_BLOCK - 1) / PACK_BLOCK), 128, 0, ctx->stream>>>(K);
+                pack_bases_kernel<<<1, 128, 0, ctx->stream>>>(K);
+                compact_copy_kernel<<<(unsigned)((count * 32 + 127) / 128), 128, 0, ctx->stream>>>(K);
+                SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+                ctx->timing.kernel_launches += 3;
+                SA_TRY(cudaEventRecord(s.packed, ctx->stream), SA_ERR_LAUNCH);
+                if (c >= 2) { rc = drain(c - 2); if (rc) return rc; }
+            }
+            if (pack) for (uint64_t k = c >= 2 ? c - 2 : 0; k < c; ++k) { rc = drain(k); if (rc) return rc; }
+            cudaStreamWaitEvent(ctx->stream, ctx->slot[(c - 1) % NSLOT].out, 0);      // stOut is in order: the last chunk's drain ends it
+        }
         int si = 0;
-        for (uint64_t first = 0; first < N; first += chunk, si = (si + 1) % NSLOT) {
+        for (uint64_t first = 0; !staged && first < N; first += chunk, si = (si + 1) % NSLOT) {
             Slot &s = ctx->slot[si];
             const uint64_t count = std::min<uint64_t>(chunk, N - first);
             const int64_t tb = to[first], pb = po[first];
@@ -1451,6 +1676,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             SA_TRY(cudaMemcpyAsync(out->aligned_text + (tb - to[0]) + (pb - po[0]), s.outT.p, arena, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(out->aligned_pattern + (tb - to[0]) + (pb - po[0]), s.outP.p, arena, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaEventRecord(s.done, s.stream), SA_ERR_LAUNCH);
+            d2hBytes += count * (sizeof(sa_result) + 8) + 2 * arena;
         }
         for (auto &s : ctx->slot) SA_TRY(cudaStreamSynchronize(s.stream), SA_ERR_LAUNCH);
         cudaEventRecord(ctx->ev[4], ctx->stream);
@@ -1525,6 +1751,8 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         if (firstErr.load()) return firstErr.load();
         tm.total_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     }
+    tm.h2d_bytes = (uint64_t)(to[N] - to[0]) + (uint64_t)(po[N] - po[0]) + 16 * (N + 1);
+    tm.d2h_bytes = d2hBytes;
     ctx->timing = tm;
     ctx->timing_dirty = false;
     return SA_OK;

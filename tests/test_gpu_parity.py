@@ -480,3 +480,37 @@ def test_host_batch_of_medium_pairs_runs_concurrently(sa, aligner, oracle):
         for i in range(14):
             assert_same(sa.unpack_batch(out, i), oracle.align(mode, 4, blast, 5, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]),
                         ("medium batch", mode, i))
+
+
+def test_host_batch_staged_pipeline_equals_slot_pipeline(sa, aligner, oracle):
+    """The host pipelines of sa_align_batch (staged: one fill stream + traceback / copy streams, strings packed on the
+    device before the copy or copied as whole slots; slots: one stream per chunk) return the same results and strings
+    on a 20 011-pair batch with ragged chunk sizes, and a sample equals the oracle."""
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(20011, seed=4242)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    rng = np.random.default_rng(5)
+    keys = ("SA_HOST_PIPELINE", "SA_HOST_CHUNKS", "SA_HOST_PACK")
+    for mode in (0, 1):
+        outs = {}
+        for cfg in (("staged", "5", "1"), ("staged", "5", "0"), ("slots", "5", "1"), ("staged", "3", "1"), ("staged", "1", "1")):
+            os.environ.update(dict(zip(keys, cfg)))
+            try:
+                outs[cfg] = aligner.align_batch(mode, 23, mat, 5, T, toff, P, poff)
+            finally:
+                for k in keys:
+                    os.environ.pop(k, None)
+        a = outs["staged", "5", "1"]
+        total = int(a["results"]["aln_len"].sum())
+        # packed: pair p's strings start where pair p-1's end
+        assert np.array_equal(a["aln_off"], np.concatenate(([0], np.cumsum(a["results"]["aln_len"])[:-1])).astype(np.uint64))
+        assert aligner.timing()["d2h_bytes"] == 40 * 20011 + 2 * total
+        for key, o in outs.items():
+            for f in ("score", "aln_len", "start_text", "start_pattern"):      # (not the struct's padding word)
+                assert np.array_equal(o["results"][f], a["results"][f]), (mode, key, f)
+        for i in list(range(0, 20011, 53)) + [20010]:
+            ka = sa.unpack_batch(a, i).key()
+            for key, o in outs.items():
+                assert sa.unpack_batch(o, i).key() == ka, (mode, key, i)
+        for i in rng.integers(0, 20011, 60):
+            assert_same(sa.unpack_batch(a, int(i)), oracle.align(mode, 23, mat, 5, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]), (mode, int(i)))

@@ -1493,13 +1493,32 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
     uint32_t max_n = 0, max_m = 0;
     uint64_t cells = 0;
     std::vector<uint64_t> longPairs;
-    for (uint64_t p = 0; p < N; ++p) {
-        const uint64_t n = (uint64_t)(to[p + 1] - to[p]), m = (uint64_t)(po[p + 1] - po[p]);
-        if (n == 0 || m == 0) return SA_ERR_ARGUMENT;
-        cells += (n + 1) * (m + 1);
-        if (wideScores || !batch_eligible(n, m)) { longPairs.push_back(p); continue; }
-        max_n = std::max<uint32_t>(max_n, (uint32_t)n);
-        max_m = std::max<uint32_t>(max_m, (uint32_t)m);
+    {
+        // one pass over the offsets (cell count, longest members, members for the long-pair kernels); big batches split it
+        // over a few host threads -- at 1 M pairs the single-threaded pass was ~1.5 ms in front of the first copy
+        struct Part { uint64_t cells = 0; uint32_t max_n = 0, max_m = 0; bool bad = false; std::vector<uint64_t> longs; };
+        const unsigned nT = N >= 262144 ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+        std::vector<Part> part(nT);
+        auto scan = [&](unsigned t) {
+            Part &P = part[t];
+            for (uint64_t p = N * t / nT, e = N * (t + 1) / nT; p < e; ++p) {
+                const uint64_t n = (uint64_t)(to[p + 1] - to[p]), m = (uint64_t)(po[p + 1] - po[p]);
+                if (n == 0 || m == 0) { P.bad = true; return; }
+                P.cells += (n + 1) * (m + 1);
+                if (wideScores || !batch_eligible(n, m)) { P.longs.push_back(p); continue; }
+                P.max_n = std::max<uint32_t>(P.max_n, (uint32_t)n);
+                P.max_m = std::max<uint32_t>(P.max_m, (uint32_t)m);
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nT; ++t) th.emplace_back(scan, t);
+        scan(0);
+        for (auto &t : th) t.join();
+        for (const Part &P : part) {
+            if (P.bad) return SA_ERR_ARGUMENT;
+            cells += P.cells; max_n = std::max(max_n, P.max_n); max_m = std::max(max_m, P.max_m);
+            longPairs.insert(longPairs.end(), P.longs.begin(), P.longs.end());
+        }
     }
     int rc = upload_scoring(ctx, sc, ctx->stream);
     if (rc) return rc;
@@ -1527,14 +1546,32 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         const bool staged = !(hp && std::strcmp(hp, "slots") == 0) && N >= 8192;
         if (staged) {
             const cudaStream_t stIn = ctx->slot[0].stream, stOut = ctx->slot[1].stream, stFill = ctx->slot[2].stream;
+            // two direction sets of the device pipeline's size (the slot pipeline's third of 8 GB made 15 chunks of 1 M
+            // pairs, whose fills add up to 29.4 ms against 25.4 ms in 5-8 chunks)
+            chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / perPair));
+            chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, (N + nChunks - 1) / nChunks));
             chunk = std::min<uint64_t>(chunk, N);
             const uint64_t nc = (N + chunk - 1) / chunk;
             chunk = (N + nc - 1) / nc;                                   // equal chunks
+            // Chunk boundaries.  Nothing overlaps the first chunk's copy in or the last chunk's traceback and copy out, so
+            // big batches start and end with small chunks: 1/32, 2/32, 3/32 of the batch, eighths in the middle, then
+            // 3/32, 2/32, 1/32 (SA_HOST_CHUNKS selects equal chunks instead).
+            std::vector<uint64_t> bounds{0};
+            if (!std::getenv("SA_HOST_CHUNKS") && N >= 65536 && chunk >= N / 8) {
+                static const int w[] = {1, 2, 3, 4, 4, 4, 4, 4, 3, 2, 1};
+                uint64_t acc = 0;
+                for (int k : w) { acc += k; bounds.push_back(acc == 32 ? N : N * acc / 32); }
+                chunk = 0;
+                for (size_t k = 1; k < bounds.size(); ++k) chunk = std::max(chunk, bounds[k] - bounds[k - 1]);
+            } else {
+                for (uint64_t first = chunk; first < N; first += chunk) bounds.push_back(first);
+                bounds.push_back(N);
+            }
+            const uint64_t nChunk = bounds.size() - 1;
             uint64_t maxT = 0, maxP = 0;
-            for (uint64_t first = 0; first < N; first += chunk) {
-                const uint64_t count = std::min<uint64_t>(chunk, N - first);
-                maxT = std::max<uint64_t>(maxT, (uint64_t)(to[first + count] - to[first]));
-                maxP = std::max<uint64_t>(maxP, (uint64_t)(po[first + count] - po[first]));
+            for (uint64_t k = 0; k < nChunk; ++k) {
+                maxT = std::max<uint64_t>(maxT, (uint64_t)(to[bounds[k + 1]] - to[bounds[k]]));
+                maxP = std::max<uint64_t>(maxP, (uint64_t)(po[bounds[k + 1]] - po[bounds[k]]));
             }
             // buffers at their final size before anything is in flight (growing one frees it, which waits for the device)
             for (auto &s : ctx->slot) {
@@ -1569,7 +1606,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             uint64_t hostBase = 0;
             auto drain = [&](uint64_t k) -> int {          // device->host copies of chunk k, sized by its packed total
                 Slot &s = ctx->slot[k % NSLOT];
-                const uint64_t first = k * chunk, count = std::min<uint64_t>(chunk, N - first);
+                const uint64_t first = bounds[k], count = bounds[k + 1] - first;
                 SA_TRY(cudaEventSynchronize(s.packed), SA_ERR_LAUNCH);
                 const uint64_t total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p)[k % NSLOT];
                 if (hostBase + total > out->arena_capacity) return SA_ERR_CAPACITY;
@@ -1585,10 +1622,10 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 return SA_OK;
             };
             uint64_t c = 0;
-            for (uint64_t first = 0; first < N; first += chunk, ++c) {
+            for (; c < nChunk; ++c) {
                 Slot &s = ctx->slot[c % NSLOT];
                 const int d = (int)(c & 1);
-                const uint64_t count = std::min<uint64_t>(chunk, N - first);
+                const uint64_t first = bounds[c], count = bounds[c + 1] - first;
                 const int64_t tb = to[first], pb = po[first];
                 const uint64_t tbytes = (uint64_t)(to[first + count] - tb), pbytes = (uint64_t)(po[first + count] - pb);
                 const uint64_t arena = tbytes + pbytes;
@@ -1604,7 +1641,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 char *oT = s.outT.as<char>() - (tb + pb), *oP = s.outP.as<char>() - (tb + pb);
                 rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
                                    ctx->pdirs[d].as<uint32_t>(), ctx->pdirs[d].cap / 4, s.fill.p, ctx->psort[d].p, &ctx->snapbuf,
-                                   stFill, 0, (uint32_t)count, ctx->stream, ctx->evFill[d], /*tbShare=*/first + chunk < N);
+                                   stFill, 0, (uint32_t)count, ctx->stream, ctx->evFill[d], /*tbShare=*/c + 1 < nChunk);
                 if (rc) return rc;
                 SA_TRY(cudaEventRecord(ctx->evTrace[d], ctx->stream), SA_ERR_LAUNCH);
                 if (!pack) {

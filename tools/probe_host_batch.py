@@ -1,0 +1,40 @@
+"""Where the host-buffer batch call spends its time: wall clock of the call vs the device span between the
+first and last event (sa_timing.total_us), for a few chunk counts.  python tools/probe_host_batch.py [pairs]"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sequence-alignment-gpu_b200"))
+import torch
+from __graft_entry__ import load_package
+import synth
+sa = load_package()
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+T, toff, P, poff = synth.synthetic_batch(N, seed=2024)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers
+mat = helpers.matrices()["protein/blosum62.txt"]
+pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+T, toff, P, poff = pin(T), pin(toff), pin(P), pin(poff)
+arena = int(toff[-1] + poff[-1])
+out = dict(results=torch.zeros(N * 4, dtype=torch.int64).pin_memory().numpy().view(sa.RESULT_DTYPE),
+           aln_off=torch.zeros(N, dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+           aligned_text=torch.empty(arena, dtype=torch.uint8).pin_memory().numpy(),
+           aligned_pattern=torch.empty(arena, dtype=torch.uint8).pin_memory().numpy())
+al = sa.Aligner(0)
+for env in ({}, {"SA_HOST_CHUNKS": "8"}, {"SA_HOST_CHUNKS": "10"},
+            {"SA_HOST_PACK": "0"}):
+    os.environ.update(env)
+    a2 = sa.Aligner(0) if "SA_TB_BLOCKS_PER_SM" in env else al
+    best = (1e9, None)
+    for _ in range(6):
+        t0 = time.perf_counter()
+        a2.align_batch(1, 23, mat, 5, T, toff, P, poff, out=out)
+        dt = (time.perf_counter() - t0) * 1e3
+        t = a2.timing()
+        if dt < best[0]:
+            best = (dt, t)
+    dt, t = best
+    print(env or "default", f"wall {dt:.2f} ms  device span {t['total_us'] / 1e3:.2f} ms  fill {t['fill_us'] / 1e3:.2f}  traceback {t['traceback_us'] / 1e3:.2f}"
+          f"  d2h {t['d2h_bytes'] / 1e6:.0f} MB", flush=True)
+    for k in env:
+        os.environ.pop(k, None)

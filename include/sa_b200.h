@@ -218,7 +218,11 @@ uint64_t sa_pretty_print(const char *aligned_text, const char *aligned_pattern, 
  * for pattern.  Aligned strings of pair p are written to
  *   aligned_text   [aln_off[p] .. aln_off[p] + results[p].aln_len)
  * where aln_off is an OUTPUT array of n_pairs entries and the two output
- * arenas must hold text_off[n_pairs] + pattern_off[n_pairs] bytes each. */
+ * arenas must hold text_off[n_pairs] + pattern_off[n_pairs] bytes each.
+ * Where a pair's strings land inside the arenas is the library's choice --
+ * read aln_off: big host batches come back packed (pair p+1 right behind pair
+ * p; only the used bytes cross PCIe), other calls leave every pair in its own
+ * slot of text_len + pattern_len bytes. */
 typedef struct {
     uint64_t       n_pairs;
     const uint8_t *text;         const int64_t *text_off;     /* n_pairs+1 */

@@ -60,7 +60,8 @@ struct PinBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr int NSLOT = 3;   // pipeline depth of the host batch path
+constexpr int NSLOT = 3;   // pipeline depth of the host batch path (slot pipeline)
+constexpr int NIO_MAX = 5; // staged pipeline: I/O buffer sets
 
 struct Slot {              // per-chunk device buffers of the host batch path
     cudaStream_t stream = nullptr;
@@ -94,7 +95,7 @@ struct sa_context {
     cudaEvent_t evFork = nullptr, evSorted = nullptr, evJoin[NCLS_STREAMS] = {};
     DevBuf clsSnap[NCLS_STREAMS];
     PinBuf pin;
-    Slot slot[NSLOT];
+    Slot slot[NIO_MAX];
     uint32_t epoch = 0;
     bool wide = false;                      // the scoring uploaded last needs the two-plane profile
     // sub-contexts for the long members of a host batch: several medium-size pairs run side by side (each is a
@@ -1546,6 +1547,8 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         const bool staged = !(hp && std::strcmp(hp, "slots") == 0) && N >= 8192;
         if (staged) {
             const cudaStream_t stIn = ctx->slot[0].stream, stOut = ctx->slot[1].stream, stFill = ctx->slot[2].stream;
+            int NIO = 4;          // I/O buffer sets in flight (copy in | fill | traceback + pack | copy out)
+            if (const char *e = std::getenv("SA_HOST_IOSETS")) NIO = std::max(3, std::min(NIO_MAX, std::atoi(e)));
             // two direction sets of the device pipeline's size (the slot pipeline's third of 8 GB made 15 chunks of 1 M
             // pairs, whose fills add up to 29.4 ms against 25.4 ms in 5-8 chunks)
             chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / perPair));
@@ -1558,9 +1561,15 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             // 3/32, 2/32, 1/32 (SA_HOST_CHUNKS selects equal chunks instead).
             std::vector<uint64_t> bounds{0};
             if (!std::getenv("SA_HOST_CHUNKS") && N >= 65536 && chunk >= N / 8) {
-                static const int w[] = {1, 2, 3, 4, 4, 4, 4, 4, 3, 2, 1};
-                uint64_t acc = 0;
-                for (int k : w) { acc += k; bounds.push_back(acc == 32 ? N : N * acc / 32); }
+                std::vector<int> w{1, 2, 3, 4, 4, 4, 4, 4, 3, 2, 1};
+                if (const char *e = std::getenv("SA_HOST_SCHEDULE")) {          // e.g. "1,2,4,5,5,5,5,3,2": parts of the batch
+                    std::vector<int> u;
+                    for (const char *q = e; *q;) { const int v = std::atoi(q); if (v > 0) u.push_back(v); while (*q && *q != ',') ++q; if (*q) ++q; }
+                    if (!u.empty()) w = u;
+                }
+                uint64_t acc = 0, tot = 0;
+                for (int k : w) tot += k;
+                for (int k : w) { acc += k; bounds.push_back(acc == tot ? N : N * acc / tot); }
                 chunk = 0;
                 for (size_t k = 1; k < bounds.size(); ++k) chunk = std::max(chunk, bounds[k] - bounds[k - 1]);
             } else {
@@ -1574,7 +1583,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 maxP = std::max<uint64_t>(maxP, (uint64_t)(po[bounds[k + 1]] - po[bounds[k]]));
             }
             // buffers at their final size before anything is in flight (growing one frees it, which waits for the device)
-            for (auto &s : ctx->slot) {
+            for (int q = 0; q < NIO; ++q) { Slot &s = ctx->slot[q];
                 SA_TRY(s.text.reserve(maxT + 16), SA_ERR_MEMORY);
                 SA_TRY(s.pattern.reserve(maxP + 16), SA_ERR_MEMORY);
                 SA_TRY(s.toff.reserve((chunk + 1) * 8), SA_ERR_MEMORY);
@@ -1594,7 +1603,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             const char *pe = std::getenv("SA_HOST_PACK");
             const bool pack = longPairs.empty() && !(pe && pe[0] == '0');
             if (pack) {
-                for (auto &s : ctx->slot) {
+                for (int q = 0; q < NIO; ++q) { Slot &s = ctx->slot[q];
                     SA_TRY(s.packT.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
                     SA_TRY(s.packP.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
                     SA_TRY(s.noff.reserve((chunk + chunk / PACK_BLOCK + 4) * 8), SA_ERR_MEMORY);
@@ -1605,10 +1614,10 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             }
             uint64_t hostBase = 0;
             auto drain = [&](uint64_t k) -> int {          // device->host copies of chunk k, sized by its packed total
-                Slot &s = ctx->slot[k % NSLOT];
+                Slot &s = ctx->slot[k % NIO];
                 const uint64_t first = bounds[k], count = bounds[k + 1] - first;
                 SA_TRY(cudaEventSynchronize(s.packed), SA_ERR_LAUNCH);
-                const uint64_t total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p)[k % NSLOT];
+                const uint64_t total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p)[k % NIO];
                 if (hostBase + total > out->arena_capacity) return SA_ERR_CAPACITY;
                 SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
                 SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
@@ -1623,13 +1632,13 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             };
             uint64_t c = 0;
             for (; c < nChunk; ++c) {
-                Slot &s = ctx->slot[c % NSLOT];
+                Slot &s = ctx->slot[c % NIO];
                 const int d = (int)(c & 1);
                 const uint64_t first = bounds[c], count = bounds[c + 1] - first;
                 const int64_t tb = to[first], pb = po[first];
                 const uint64_t tbytes = (uint64_t)(to[first + count] - tb), pbytes = (uint64_t)(po[first + count] - pb);
                 const uint64_t arena = tbytes + pbytes;
-                if (c >= NSLOT) cudaStreamWaitEvent(stIn, s.out, 0);          // the set's previous chunk has drained
+                if (c >= (uint64_t)NIO) cudaStreamWaitEvent(stIn, s.out, 0);          // the set's previous chunk has drained
                 SA_TRY(cudaMemcpyAsync(s.text.p, b->text + tb, tbytes, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
                 SA_TRY(cudaMemcpyAsync(s.pattern.p, b->pattern + pb, pbytes, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
                 SA_TRY(cudaMemcpyAsync(s.toff.p, to + first, (count + 1) * 8, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
@@ -1660,7 +1669,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 K.results = s.results.as<sa_result>(); K.aln_off = s.alnoff.as<uint64_t>(); K.count = (uint32_t)count;
                 K.srcT = oT; K.srcP = oP; K.dstT = s.packT.as<char>(); K.dstP = s.packP.as<char>();
                 K.noff = s.noff.as<unsigned long long>(); K.running = ctx->packstate.as<unsigned long long>();
-                K.host_total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p) + (c % NSLOT);
+                K.host_total = reinterpret_cast<volatile unsigned long long *>(ctx->pin.p) + (c % NIO);
                 K.block_base = K.noff + chunk;
                 pack_local_kernel<<<(unsigned)((count + PACK_BLOCK - 1) / PACK_BLOCK), 128, 0, ctx->stream>>>(K);
                 pack_bases_kernel<<<1, 128, 0, ctx->stream>>>(K);
@@ -1671,7 +1680,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 if (c >= 2) { rc = drain(c - 2); if (rc) return rc; }
             }
             if (pack) for (uint64_t k = c >= 2 ? c - 2 : 0; k < c; ++k) { rc = drain(k); if (rc) return rc; }
-            cudaStreamWaitEvent(ctx->stream, ctx->slot[(c - 1) % NSLOT].out, 0);      // stOut is in order: the last chunk's drain ends it
+            cudaStreamWaitEvent(ctx->stream, ctx->slot[(c - 1) % NIO].out, 0);      // stOut is in order: the last chunk's drain ends it
         }
         int si = 0;
         for (uint64_t first = 0; !staged && first < N; first += chunk, si = (si + 1) % NSLOT) {

@@ -21,10 +21,10 @@ out = dict(results=torch.zeros(N * 4, dtype=torch.int64).pin_memory().numpy().vi
            aligned_text=torch.empty(arena, dtype=torch.uint8).pin_memory().numpy(),
            aligned_pattern=torch.empty(arena, dtype=torch.uint8).pin_memory().numpy())
 al = sa.Aligner(0)
-for env in ({}, {"SA_HOST_CHUNKS": "8"}, {"SA_HOST_CHUNKS": "10"},
-            {"SA_HOST_PACK": "0"}):
+for env in ({}, {"SA_HOST_IOSETS": "3"}, {"SA_HOST_IOSETS": "5"}, {"SA_HOST_SCHEDULE": "1,2,4,5,5,5,5,3,2"},
+            {"SA_HOST_SCHEDULE": "1,2,3,3,3,3,3,3,3,3,2,2,1"}, {"SA_HOST_SCHEDULE": "1,2,4,6,6,6,4,2,1", "SA_HOST_IOSETS": "5"}):
     os.environ.update(env)
-    a2 = sa.Aligner(0) if "SA_TB_BLOCKS_PER_SM" in env else al
+    a2 = al
     best = (1e9, None)
     for _ in range(6):
         t0 = time.perf_counter()

@@ -107,6 +107,12 @@ def lib() -> C.CDLL:
             raise FileNotFoundError(f"{LIB_PATH} is missing: run __graft_entry__.build() / make -C {CSRC}")
         L = C.CDLL(LIB_PATH)
         L.sa_version.restype = C.c_char_p
+        L.sa_host_alloc.restype = C.c_void_p
+        L.sa_host_alloc.argtypes = [C.c_uint64]
+        L.sa_host_free.restype = None
+        L.sa_host_free.argtypes = [C.c_void_p]
+        L.sa_host_register.argtypes = [C.c_void_p, C.c_uint64]
+        L.sa_host_unregister.argtypes = [C.c_void_p]
         L.sa_status_string.restype = C.c_char_p
         L.sa_status_string.argtypes = [C.c_int]
         L.sa_device_count.restype = C.c_int
@@ -323,6 +329,38 @@ class Aligner:
         o = _BatchOut(d_results, d_aln_off, d_out_text, d_out_pattern, arena_capacity)
         self._check(self._L.sa_align_batch_device(self._ctx, C.byref(sc), C.byref(b), C.byref(o),
                                                   int(max_text_len), int(max_pattern_len), C.c_void_p(stream)))
+
+
+class _PinnedOwner:
+    """Frees a sa_host_alloc block when the last numpy view of it goes away."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().sa_host_alloc(int(nbytes))
+        if not self.ptr:
+            raise SaError(-2, "pinned host allocation failed")
+
+    def __del__(self):
+        try:
+            lib().sa_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array in page-locked host memory (sa_host_alloc): the buffers sa_align_batch copies at PCIe speed."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    owner = _PinnedOwner(max(1, n * dtype.itemsize))
+    buf = (C.c_ubyte * max(1, n * dtype.itemsize)).from_address(owner.ptr)
+    buf._owner = owner                       # array -> ctypes buffer -> owner: freed with the last view
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 def unpack_batch(out, i) -> Alignment:

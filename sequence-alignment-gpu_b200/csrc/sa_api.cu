@@ -935,6 +935,28 @@ extern "C" {
 
 const char *sa_version(void) { return "sa_b200 0.1 (sm_100a)"; }
 
+// Page-locked host buffers for the callers of sa_align_batch / sa_align: the copies of a call run at PCIe speed only
+// from pinned memory (pageable buffers go through the driver's bounce buffer at a fraction of it).
+void *sa_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void sa_host_free(void *p) { if (p) cudaFreeHost(p); }
+int sa_host_register(void *p, uint64_t bytes)
+{
+    if (!p || !bytes) return SA_ERR_ARGUMENT;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return SA_ERR_MEMORY; }
+    return SA_OK;
+}
+int sa_host_unregister(void *p)
+{
+    if (!p) return SA_ERR_ARGUMENT;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return SA_ERR_ARGUMENT; }
+    return SA_OK;
+}
+
 const char *sa_status_string(int s)
 {
     switch (s) {

@@ -514,3 +514,25 @@ def test_host_batch_staged_pipeline_equals_slot_pipeline(sa, aligner, oracle):
                 assert sa.unpack_batch(o, i).key() == ka, (mode, key, i)
         for i in rng.integers(0, 20011, 60):
             assert_same(sa.unpack_batch(a, int(i)), oracle.align(mode, 23, mat, 5, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]), (mode, int(i)))
+
+
+def test_pinned_host_buffers(sa, aligner, oracle):
+    """sa_host_alloc / sa_host_register: a batch in page-locked buffers gives the same answers as in pageable ones."""
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(9000, seed=99)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    ref = aligner.align_batch(1, 23, mat, 5, T, toff, P, poff)
+    arena = int(toff[-1] + poff[-1])
+    out = dict(results=sa.pinned_empty(9000, sa.RESULT_DTYPE), aln_off=sa.pinned_empty(9000, np.uint64),
+               aligned_text=sa.pinned_empty(arena, np.uint8), aligned_pattern=sa.pinned_empty(arena, np.uint8))
+    got = aligner.align_batch(1, 23, mat, 5, sa.pinned_copy(T), sa.pinned_copy(toff), sa.pinned_copy(P), sa.pinned_copy(poff), out=out)
+    for i in range(0, 9000, 7):
+        assert sa.unpack_batch(got, i).key() == sa.unpack_batch(ref, i).key(), i
+    i = 4321
+    assert_same(sa.unpack_batch(got, i), oracle.align(1, 23, mat, 5, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]]), i)
+    # registering an existing buffer, and the error paths
+    buf = np.zeros(1 << 20, np.uint8)
+    assert sa.lib().sa_host_register(buf.ctypes.data, buf.nbytes) == 0
+    assert sa.lib().sa_host_unregister(buf.ctypes.data) == 0
+    assert sa.lib().sa_host_register(None, 16) != 0
+    del out, got

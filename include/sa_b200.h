@@ -36,7 +36,10 @@ typedef enum {
     SA_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
     SA_ERR_MEMORY = -2,      /* device or pinned allocation failed (reference: MEM_ERROR, alignSequenceGPU.cu:541-546) */
     SA_ERR_COPY = -3,        /* host<->device copy failed (reference: "could not copy from device memory", :588-594) */
-    SA_ERR_ARGUMENT = -4,    /* null pointer, empty sequence, residue >= alphabet_size, alphabet_size > 32 ... */
+    SA_ERR_ARGUMENT = -4,    /* null pointer, empty sequence, alphabet_size > 32, ...; from the HOST-buffer entry points
+                              * (sa_align, sa_fill_only, sa_align_batch) also a residue >= alphabet_size.  The
+                              * device-resident entry points do not scan their inputs: there such a residue is
+                              * read as letter alphabet_size-1 (clamped, never out of bounds). */
     SA_ERR_SCORE_RANGE = -5, /* |score| > 4064 or gap > 2^24; also: a matrix beyond +-31 given to the device-resident
                               * batch / slice entry points (such matrices run through the single-pair kernels only) */
     SA_ERR_LAUNCH = -6,      /* kernel launch / execution error */
@@ -246,7 +249,9 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *scoring,
  * pointer (e.g. torch tensors' data_ptr()), work is enqueued on `stream`
  * (a cudaStream_t used as given; NULL is the CUDA default stream) and the call
  * returns without synchronising.  max_text_len / max_pattern_len bound the pair sizes (they
- * size the direction workspace). */
+ * size the direction workspace).  A pair with an empty side, a text longer than max_text_len or a
+ * pattern longer than max_pattern_len is not aligned: its result is the sentinel
+ * {score INT32_MIN, aln_len 0, starts 0} and aln_off 0. */
 int sa_align_batch_device(sa_context *ctx, const sa_scoring *scoring,
                           const sa_batch *batch, sa_batch_out *out,
                           uint32_t max_text_len, uint32_t max_pattern_len,

@@ -112,10 +112,46 @@ class Oracle:
             raise MemoryError
         return score.value, arg.value
 
+    def check_batch(self, mode, alpha, matrix, gap, text, text_off, pattern, pattern_off, out, idx=None, nthreads=0):
+        """Every Response field and both strings of the pairs ``idx`` (default: all) of a sa_align_batch-style result
+        ``out`` (results / aln_off / aligned_text / aligned_pattern arrays) against sa_oracle_align, on ``nthreads``
+        host threads (0 = all).  Returns (mismatching pairs, first mismatching pair or -1)."""
+        return _check_batch(self.lib.sa_oracle_check_batch, True, mode, alpha, matrix, gap, text, text_off, pattern,
+                            pattern_off, out, idx, nthreads)
+
     def rescore(self, aligned_text: bytes, aligned_pattern: bytes, alpha, matrix, gap) -> int:
         matrix = _i32(matrix)
         return self.lib.sa_oracle_rescore(aligned_text, aligned_pattern, len(aligned_text),
                                           alphabet_for(alpha), alpha, matrix.ctypes.data, gap)
+
+
+def _check_batch(fn, with_alphabet, mode, alpha, matrix, gap, text, text_off, pattern, pattern_off, out, idx, nthreads):
+    text, pattern = _u8(text), _u8(pattern)
+    toff = np.ascontiguousarray(text_off, dtype=np.int64)
+    poff = np.ascontiguousarray(pattern_off, dtype=np.int64)
+    full = np.zeros(max(23 * 23, alpha * alpha), np.int32)
+    full[:alpha * alpha] = _i32(matrix).ravel()[:alpha * alpha]
+    N = len(toff) - 1
+    if idx is None:
+        pidx, nidx = None, N
+    else:
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        pidx, nidx = idx.ctypes.data, len(idx)
+    res = np.ascontiguousarray(out["results"])
+    assert res.dtype.itemsize == 32 and len(res) >= N
+    aoff = np.ascontiguousarray(out["aln_off"], dtype=np.uint64)
+    aT, aP = np.ascontiguousarray(out["aligned_text"]), np.ascontiguousarray(out["aligned_pattern"])
+    first = C.c_int64(-1)
+    fn.restype = C.c_uint64
+    args = [C.c_int(mode), C.c_int(alpha), C.c_void_p(full.ctypes.data), C.c_int(gap)]
+    if with_alphabet:
+        args.append(C.c_char_p(alphabet_for(alpha)))
+    args += [C.c_void_p(text.ctypes.data), C.c_void_p(toff.ctypes.data), C.c_void_p(pattern.ctypes.data),
+             C.c_void_p(poff.ctypes.data), C.c_void_p(pidx), C.c_uint64(nidx), C.c_void_p(res.ctypes.data),
+             C.c_void_p(aoff.ctypes.data), C.c_void_p(aT.ctypes.data), C.c_void_p(aP.ctypes.data),
+             C.c_int(nthreads or (os.cpu_count() or 1)), C.byref(first)]
+    bad = fn(*args)
+    return int(bad), int(first.value)
 
 
 class Reference:
@@ -190,6 +226,11 @@ class Reference:
         if bad:
             raise MemoryError(f"{bad} pairs failed in the reference")
         return scores, lens
+
+    def check_batch(self, mode, alpha, matrix, gap, text, text_off, pattern, pattern_off, out, idx=None, nthreads=0):
+        """Like Oracle.check_batch, but the truth is the UNMODIFIED alignSequenceCPU (ref_check_batch)."""
+        return _check_batch(self.lib.ref_check_batch, False, mode, alpha, matrix, gap, text, text_off, pattern,
+                            pattern_off, out, idx, nthreads)
 
     def fill(self, mode, alpha, matrix, gap, text, pattern, M=None):
         text, pattern = _u8(text), _u8(pattern)

@@ -92,6 +92,49 @@ int ref_align_cpu_batch(int mode, int alphabetSize, const int *matrix, int gap,
     return failed.load();
 }
 
+// The same loop as a CHECKER (tests/, bench.py "verified"): every Response field and both strings of the listed pairs,
+// computed by the unmodified alignSequenceCPU, against a result set laid out like sa_align_batch's (results[p] =
+// {int32 score, pad, u64 aln_len, u64 start_text, u64 start_pattern}; strings at aligned_*[aln_off[p] ..)).
+// idx == nullptr checks pairs 0..nIdx-1.  Returns the number of mismatching pairs, *firstBad the smallest one or -1.
+// Pairs whose pattern is longer than their text are aligned with the operands as given; the reference's 2*text output
+// capacity (alignSequenceCPU.cpp:306-307) holds for the mutate.py-style batches this is used on.
+uint64_t ref_check_batch(int mode, int alphabetSize, const int *matrix, int gap,
+                         const char *text, const int64_t *toff, const char *pattern, const int64_t *poff,
+                         const uint64_t *idx, uint64_t nIdx, const void *results, const uint64_t *alnOff,
+                         const char *alnT, const char *alnP, int nthreads, int64_t *firstBad)
+{
+    struct Res { int32_t score; int32_t pad; uint64_t len, st, sp; };
+    const Res *R = static_cast<const Res *>(results);
+    std::atomic<uint64_t> next(0), bad(0);
+    std::atomic<int64_t> first(-1);
+    auto worker = [&]() {
+        for (;;) {
+            const uint64_t k = next.fetch_add(1);
+            if (k >= nIdx) break;
+            const uint64_t p = idx ? idx[k] : k;
+            const uint64_t n = (uint64_t)(toff[p + 1] - toff[p]), m = (uint64_t)(poff[p + 1] - poff[p]);
+            SequenceAlignment::Request rq;
+            SequenceAlignment::Response rs;
+            fillRequest(rq, mode, alphabetSize, matrix, gap, text + toff[p], n, pattern + poff[p], m);
+            bool ok = SequenceAlignment::alignSequenceCPU(rq, &rs) == 0;
+            ok = ok && R[p].score == rs.score && R[p].len == rs.numAlignmentBytes && R[p].st == rs.startInAlignedText &&
+                 R[p].sp == rs.startInAlignedPattern &&
+                 std::memcmp(alnT + alnOff[p], rs.alignedTextBytes, rs.numAlignmentBytes) == 0 &&
+                 std::memcmp(alnP + alnOff[p], rs.alignedPatternBytes, rs.numAlignmentBytes) == 0;
+            if (!ok) {
+                bad++;
+                int64_t cur = first.load();
+                while ((cur < 0 || (int64_t)p < cur) && !first.compare_exchange_weak(cur, (int64_t)p)) {}
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < (nthreads > 1 ? nthreads : 1); ++t) th.emplace_back(worker);
+    for (auto &t : th) t.join();
+    if (firstBad) *firstBad = first.load();
+    return bad.load();
+}
+
 // Fill only (file-local fillMatrixNW / fillMatrixSW, alignSequenceCPU.cpp:203,116):
 // what tests/benchmarks.cu:150-157 times as the CPU "MCUPS".  M = (m+1)*(n+1) bytes.
 int ref_fill_cpu(int mode, int alphabetSize, const int *matrix, int gap,

@@ -20,6 +20,7 @@
  *   gap is a positive magnitude that is subtracted.
  *   DIRECTION { LEFT=0, DIAG=1, TOP=2, STOP=3 } (SequenceAlignment.hpp:122).
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -244,4 +245,75 @@ int64_t sa_oracle_rescore(const char *alnT, const char *alnP, uint64_t len,
         else total += S[idx[(unsigned char)alnP[k]] * alpha + idx[(unsigned char)alnT[k]]];
     }
     return total;
+}
+
+/* ---- batch checker (tests/, bench.py "verified"): aligns the listed pairs of a CSR batch with sa_oracle_align on
+ * `nthreads` host threads and compares EVERY Response field and both strings (alignSequenceCPU.cpp:287-333 is the
+ * truth) with a result set laid out like sa_align_batch's: results[p] = {int32 score, pad, u64 aln_len, u64
+ * start_text, u64 start_pattern}, strings of pair p at aligned_*[aln_off[p] .. + aln_len).  idx == NULL checks pairs
+ * 0..n_idx-1.  Returns the number of mismatching pairs; *first_bad (may be NULL) receives the smallest such pair
+ * index or -1. */
+typedef struct {
+    int mode, alpha, g; const int32_t *S; const char *alphabet;
+    const uint8_t *text; const int64_t *toff; const uint8_t *pattern; const int64_t *poff;
+    const uint64_t *idx; uint64_t n_idx;
+    const sa_oracle_result *results; const uint64_t *aln_off; const char *alnT; const char *alnP;
+    uint64_t next; uint64_t bad; int64_t first_bad;
+    pthread_mutex_t mu;
+} check_job;
+
+static void *check_worker(void *arg)
+{
+    check_job *J = (check_job *)arg;
+    char *oT = NULL, *oP = NULL; uint64_t cap = 0;
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        const uint64_t k0 = J->next; J->next += 16;
+        pthread_mutex_unlock(&J->mu);
+        if (k0 >= J->n_idx) break;
+        for (uint64_t k = k0; k < k0 + 16 && k < J->n_idx; ++k) {
+            const uint64_t p = J->idx ? J->idx[k] : k;
+            const uint64_t n = (uint64_t)(J->toff[p + 1] - J->toff[p]), m = (uint64_t)(J->poff[p + 1] - J->poff[p]);
+            if (n + m + 1 > cap) { cap = 2 * (n + m) + 64; free(oT); free(oP); oT = (char *)malloc(cap); oP = (char *)malloc(cap); }
+            sa_oracle_result r; memset(&r, 0, sizeof r);
+            int ok = oT && oP && sa_oracle_align(J->mode, J->alpha, J->S, J->g, J->alphabet, J->text + J->toff[p], n,
+                                                 J->pattern + J->poff[p], m, oT, oP, &r, NULL) == 0;
+            const sa_oracle_result *g = &J->results[p];
+            ok = ok && g->score == r.score && g->aln_len == r.aln_len && g->start_text == r.start_text &&
+                 g->start_pattern == r.start_pattern &&
+                 memcmp(J->alnT + J->aln_off[p], oT, r.aln_len) == 0 && memcmp(J->alnP + J->aln_off[p], oP, r.aln_len) == 0;
+            if (!ok) {
+                pthread_mutex_lock(&J->mu);
+                J->bad++;
+                if (J->first_bad < 0 || (int64_t)p < J->first_bad) J->first_bad = (int64_t)p;
+                pthread_mutex_unlock(&J->mu);
+            }
+        }
+    }
+    free(oT); free(oP);
+    return NULL;
+}
+
+uint64_t sa_oracle_check_batch(int mode, int alpha, const int32_t *S, int g, const char *alphabet,
+                               const uint8_t *text, const int64_t *toff, const uint8_t *pattern, const int64_t *poff,
+                               const uint64_t *idx, uint64_t n_idx, const void *results, const uint64_t *aln_off,
+                               const char *alnT, const char *alnP, int nthreads, int64_t *first_bad)
+{
+    check_job J;
+    memset(&J, 0, sizeof J);
+    J.mode = mode; J.alpha = alpha; J.g = g; J.S = S; J.alphabet = alphabet;
+    J.text = text; J.toff = toff; J.pattern = pattern; J.poff = poff; J.idx = idx; J.n_idx = n_idx;
+    J.results = (const sa_oracle_result *)results; J.aln_off = aln_off; J.alnT = alnT; J.alnP = alnP;
+    J.first_bad = -1;
+    pthread_mutex_init(&J.mu, NULL);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < nthreads - 1; ++t) if (pthread_create(&th[started], NULL, check_worker, &J) == 0) ++started;
+    check_worker(&J);
+    for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&J.mu);
+    if (first_bad) *first_bad = J.first_bad;
+    return J.bad;
 }

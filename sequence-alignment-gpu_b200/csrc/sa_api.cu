@@ -87,6 +87,7 @@ struct sa_context {
     // device-batch pipeline: fills on the caller's stream, tracebacks on `stream`, two buffer sets
     DevBuf pdirs[2], psort[2];
     DevBuf packstate;                     // staged host path: running total of the packed strings
+    DevBuf errflag;                       // host batch: set by validate_residues_kernel
     cudaEvent_t evFill[2] = {}, evTrace[2] = {};
     // the class kernels of one chunk are independent: they run on side streams so that the tail of
     // one class overlaps the body of the next
@@ -292,7 +293,7 @@ bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, bool line, 
         T->stride[k] = batch_task_stride(c, max_n, T->packed[k]);
         if ((uint32_t)(c.R * c.L) >= max_m) break;      // larger classes cannot occur
     }
-    T->max_text = BATCH_MAX_TEXT;
+    T->max_text = std::min<uint32_t>(BATCH_MAX_TEXT, max_n);      // windows, strides and the dirs bound are sized from max_n
     int shift = 0;
     while ((max_n >> shift) >= (uint32_t)SORT_BUCKETS) ++shift;
     T->bucket_shift = shift;
@@ -437,6 +438,35 @@ int occupancy_batch(const BatchCfg &cfg, bool local, size_t smem)
     return 0;
 }
 
+// ---- residue validation (sa_b200.h: a residue >= alphabet_size is SA_ERR_ARGUMENT) ----
+// The kernels clamp letters to alphabet_size-1 while staging, so a bad byte never indexes out of bounds; the host
+// entry points still refuse such input.  Single pairs are scanned on the host (a few hundred KB); the chunks of a
+// host batch are scanned on the device right behind their copy (600 MB per 1 M pairs would cost the host tens of ms).
+__global__ void __launch_bounds__(256) validate_residues_kernel(const uint8_t *p, const size_t n, const unsigned alpha, int *flag)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    unsigned worst = 0;
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)p & 15)) & 15));
+    if (tid < head) worst = p[tid];
+    const uint4 *q = reinterpret_cast<const uint4 *>(p + head);
+    const size_t nv = (n - head) / 16;
+    for (size_t i = tid; i < nv; i += nthreads) {
+        const uint4 v = q[i];
+        const unsigned m = __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w));
+        worst = max(worst, max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24)));
+    }
+    const size_t tail = head + nv * 16;
+    if (tail + tid < n) worst = max(worst, (unsigned)p[tail + tid]);
+    if (worst >= alpha) *flag = 1;
+}
+
+bool residues_ok(const uint8_t *p, uint64_t n, int alpha)
+{
+    unsigned worst = 0;
+    for (uint64_t i = 0; i < n; ++i) worst = std::max<unsigned>(worst, p[i]);      // vectorised by the compiler
+    return worst < (unsigned)alpha;
+}
+
 // ---- staged host path: strings of a chunk packed back to back before they cross PCIe ----
 // The traceback writes pair p's strings at the END of its slot of text_len + pattern_len bytes (it walks backwards and
 // does not know the length in advance), so a chunk's arenas are about half slack.  These kernels pack the used
@@ -558,6 +588,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     S.key = S.hist + MAX_CLASSES * SORT_BUCKETS;
     S.order = S.key + count;
     S.dyn = reinterpret_cast<BatchClassDyn *>(reinterpret_cast<char *>(S.order + count) + ((8 - ((uintptr_t)(S.order + count) & 7)) & 7));
+    S.skipped_results = d_results; S.skipped_alnoff = reinterpret_cast<unsigned long long *>(d_alnoff);
     // With SA_BATCH_CLASS_STREAMS (default on for big chunks) the binning and the class kernels run on the context's
     // HIGH-PRIORITY side streams (fork/join by events): the classes run concurrently, and none of it queues behind the
     // traceback blocks of the previous chunk, which would otherwise hold every SM until they drain.
@@ -1058,6 +1089,7 @@ void sa_destroy(sa_context *ctx)
     for (auto &b : ctx->pdirs) b.release();
     for (auto &b : ctx->psort) b.release();
     ctx->packstate.release();
+    ctx->errflag.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1097,6 +1129,8 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
     if (n >= (1ull << 31) - 64 || m >= (1ull << 31) - 64) return SA_ERR_ARGUMENT;
     if (traceback && (!outT || !outP)) return SA_ERR_ARGUMENT;
     if (traceback && cap < n + m) return SA_ERR_CAPACITY;
+    if (sc->alphabet_size < 2 || sc->alphabet_size > MAX_ALPHA) return SA_ERR_ARGUMENT;
+    if (!residues_ok(text, n, sc->alphabet_size) || !residues_ok(pattern, m, sc->alphabet_size)) return SA_ERR_ARGUMENT;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = ctx->stream;
     reset_timing(ctx);
@@ -1553,6 +1587,14 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
     if (max_m > 0) {
         BatchClassTable T;
         if (!build_class_table(max_n, max_m, fits_s16(sc, max_n, max_m), line16_ok(sc), &T)) return SA_ERR_ARGUMENT;
+        SA_TRY(ctx->errflag.reserve(16), SA_ERR_MEMORY);
+        SA_TRY(cudaMemsetAsync(ctx->errflag.p, 0, 4, ctx->stream), SA_ERR_LAUNCH);
+        auto validate = [&](const void *d_text, uint64_t tbytes, const void *d_pat, uint64_t pbytes, cudaStream_t vst) {
+            int *flag = ctx->errflag.as<int>();
+            validate_residues_kernel<<<(unsigned)std::min<uint64_t>(4 * ctx->sms, (tbytes / 4096) + 1), 256, 0, vst>>>((const uint8_t *)d_text, tbytes, (unsigned)sc->alphabet_size, flag);
+            validate_residues_kernel<<<(unsigned)std::min<uint64_t>(4 * ctx->sms, (pbytes / 4096) + 1), 256, 0, vst>>>((const uint8_t *)d_pat, pbytes, (unsigned)sc->alphabet_size, flag);
+            ctx->timing.kernel_launches += 2;
+        };
         // chunk size: bounded by the direction budget and by ~1/8 of the batch for copy/compute overlap
         const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;
         uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->host_dirs_budget / NSLOT / perPair));
@@ -1567,6 +1609,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         // device->host copies on a fourth; everything is ordered by events, the host only waits at the end.
         const char *hp = std::getenv("SA_HOST_PIPELINE");
         const bool staged = !(hp && std::strcmp(hp, "slots") == 0) && N >= 8192;
+        bool packedOut = false;       // the strings came back packed: aln_off already counts from the start of the arenas
         if (staged) {
             const cudaStream_t stIn = ctx->slot[0].stream, stOut = ctx->slot[1].stream, stFill = ctx->slot[2].stream;
             int NIO = 4;          // I/O buffer sets in flight (copy in | fill | traceback + pack | copy out)
@@ -1624,6 +1667,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             // into their slots afterwards, which the packed layout would overlap: such batches stay unpacked.
             const char *pe = std::getenv("SA_HOST_PACK");
             const bool pack = longPairs.empty() && !(pe && pe[0] == '0');
+            packedOut = pack;
             if (pack) {
                 for (int q = 0; q < NIO; ++q) { Slot &s = ctx->slot[q];
                     SA_TRY(s.packT.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
@@ -1665,6 +1709,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 SA_TRY(cudaMemcpyAsync(s.pattern.p, b->pattern + pb, pbytes, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
                 SA_TRY(cudaMemcpyAsync(s.toff.p, to + first, (count + 1) * 8, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
                 SA_TRY(cudaMemcpyAsync(s.poff.p, po + first, (count + 1) * 8, cudaMemcpyHostToDevice, stIn), SA_ERR_COPY);
+                validate(s.text.p, tbytes, s.pattern.p, pbytes, stIn);
                 SA_TRY(cudaEventRecord(s.in, stIn), SA_ERR_LAUNCH);
                 cudaStreamWaitEvent(stFill, s.in, 0);
                 if (c >= 2) cudaStreamWaitEvent(stFill, ctx->evTrace[d], 0);  // direction set d is free again
@@ -1728,6 +1773,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             SA_TRY(cudaMemcpyAsync(s.pattern.p, b->pattern + pb, pbytes, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(s.toff.p, to + first, (count + 1) * 8, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(s.poff.p, po + first, (count + 1) * 8, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
+            validate(s.text.p, tbytes, s.pattern.p, pbytes, s.stream);
             // device-side offsets are relative to the chunk: rebase with a tiny kernel-free trick --
             // the kernels subtract nothing, so pass pointers shifted by the chunk base instead.
             sa_batch cb{count, s.text.as<uint8_t>() - tb, s.toff.as<int64_t>(), s.pattern.as<uint8_t>() - pb, s.poff.as<int64_t>()};
@@ -1749,15 +1795,21 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
         for (auto &s : ctx->slot) SA_TRY(cudaStreamSynchronize(s.stream), SA_ERR_LAUNCH);
         cudaEventRecord(ctx->ev[4], ctx->stream);
         SA_TRY(cudaStreamSynchronize(ctx->stream), SA_ERR_LAUNCH);
+        {
+            int bad = 0;
+            SA_TRY(cudaMemcpy(&bad, ctx->errflag.p, 4, cudaMemcpyDeviceToHost), SA_ERR_COPY);
+            if (bad) return SA_ERR_ARGUMENT;       // a residue >= alphabet_size somewhere in the batch
+        }
         tm.total_us = ev_us(ctx->ev[0], ctx->ev[4]);
         {
             sa_timing k{};
             sa_last_timing(ctx, &k);
             tm.fill_us = k.fill_us; tm.traceback_us = k.traceback_us; tm.kernel_launches = k.kernel_launches;
         }
-        // aln_off values are absolute (text_off+pattern_off based); make them relative to the arenas
+        // unpacked aln_off values are absolute (text_off+pattern_off based); make them relative to the arenas.  Packed
+        // ones already are: compact_copy_kernel rewrote them to positions that start at 0.
         const uint64_t base0 = (uint64_t)(to[0] + po[0]);
-        if (base0) for (uint64_t p = 0; p < N; ++p) out->aln_off[p] -= base0;
+        if (base0 && !packedOut) for (uint64_t p = 0; p < N; ++p) out->aln_off[p] -= base0;
     }
     // Long members: one by one through sa_align -- but several at a time when there are several: a pair of a few
     // thousand residues fills a fraction of the GPU (its cooperative launch has a handful of blocks), so up to

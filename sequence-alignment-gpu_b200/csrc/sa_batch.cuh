@@ -223,6 +223,9 @@ struct BatchSortArgs {
     uint32_t *key;                    // count entries
     uint32_t *order;                  // count entries (output)
     BatchClassDyn *dyn;               // n_classes + 1 entries (output)
+    // pairs no class takes (empty side, text above table.max_text, pattern above the top class) get a sentinel
+    // result {score INT32_MIN, aln_len 0} instead of stale memory; the host path aligns such members afterwards
+    sa_result *skipped_results;  unsigned long long *skipped_alnoff;
 };
 
 __global__ void __launch_bounds__(256) batch_classify_kernel(const BatchSortArgs A)
@@ -243,6 +246,11 @@ __global__ void __launch_bounds__(256) batch_classify_kernel(const BatchSortArgs
     }
     A.key[i] = key;
     if (key != 0xffffffffu) atomicAdd(&A.hist[key], 1u);
+    else if (A.skipped_results) {
+        sa_result r; r.score = (int32_t)0x80000000; r.aln_len = 0; r.start_text = 0; r.start_pattern = 0;
+        A.skipped_results[p] = r;
+        A.skipped_alnoff[p] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(1024) batch_scan_kernel(const BatchSortArgs A)

@@ -536,3 +536,122 @@ def test_pinned_host_buffers(sa, aligner, oracle):
     assert sa.lib().sa_host_unregister(buf.ctypes.data) == 0
     assert sa.lib().sa_host_register(None, 16) != 0
     del out, got
+
+
+def _device_batch(sa, al, mode, mat, T, toff, P, poff, max_n=None, max_m=None):
+    """sa_align_batch_device on torch tensors; returns the result set as host numpy arrays."""
+    import torch
+    dev = torch.device("cuda:0")
+    dT, dP = torch.from_numpy(T).to(dev), torch.from_numpy(P).to(dev)
+    dto, dpo = torch.from_numpy(toff).to(dev), torch.from_numpy(poff).to(dev)
+    N = len(toff) - 1
+    arena = int(toff[-1] + poff[-1])
+    res = torch.zeros(N * 4, dtype=torch.int64, device=dev)
+    aoff = torch.zeros(N, dtype=torch.int64, device=dev)
+    oT = torch.zeros(arena, dtype=torch.uint8, device=dev)
+    oP = torch.zeros(arena, dtype=torch.uint8, device=dev)
+    max_n = max_n or int((toff[1:] - toff[:-1]).max())
+    max_m = max_m or int((poff[1:] - poff[:-1]).max())
+    al.align_batch_device(mode, 23, mat, 5, N, dT.data_ptr(), dto.data_ptr(), dP.data_ptr(), dpo.data_ptr(),
+                          res.data_ptr(), aoff.data_ptr(), oT.data_ptr(), oP.data_ptr(), arena, max_n, max_m,
+                          stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return dict(results=res.cpu().numpy().view(sa.RESULT_DTYPE), aln_off=aoff.cpu().numpy().astype(np.uint64),
+                aligned_text=oT.cpu().numpy(), aligned_pattern=oP.cpu().numpy())
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_device_batch_pipelined_chunks_all_pairs(sa, oracle, monkeypatch, mode):
+    """The path behind the bench's `value`: sa_align_batch_device with the chunk pipeline engaged (>= 8192 pairs) and a
+    direction budget small enough for >= 5 chunks, so that fill / traceback overlap and both buffer sets are reused.
+    EVERY pair is compared field by field and string by string with the unmodified reference (all host threads),
+    and the whole result set with the host-buffer path."""
+    import synth
+    from oracle.oracle_py import Reference
+    N = 24000
+    T, toff, P, poff = synth.synthetic_batch(N, seed=777)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    monkeypatch.setenv("SA_DIRS_BUDGET_MB", "160")
+    al = sa.Aligner(0)
+    try:
+        out = _device_batch(sa, al, mode, mat, T, toff, P, poff)
+        # the chunks of the call: 4 events (fill start/end, traceback start/end) per chunk in the context's timing pool
+        launches = al.timing()["kernel_launches"]
+    finally:
+        al.close()
+    per_chunk = 3 + 1 + 9          # binning kernels, traceback, at most 9 class kernels
+    assert launches >= 5 * 5, launches          # >= 5 chunks x (3 binning + >= 1 class + 1 traceback)
+    assert launches / per_chunk < 40
+    chk = Reference("O3") if Reference.available("O3") else oracle
+    assert chk.check_batch(mode, 23, mat, 5, T, toff, P, poff, out) == (0, -1)
+    monkeypatch.delenv("SA_DIRS_BUDGET_MB")
+    al2 = sa.Aligner(0)
+    try:
+        host = al2.align_batch(mode, 23, mat, 5, T, toff, P, poff)
+    finally:
+        al2.close()
+    for f in ("score", "aln_len", "start_text", "start_pattern"):
+        assert np.array_equal(host["results"][f], out["results"][f]), f
+    # strings: the host path returns them packed, the device path in slots -- compare through a checksum of every pair
+    def digest(o):
+        ln = o["results"]["aln_len"].astype(np.int64)
+        off = o["aln_off"].astype(np.int64)
+        idx = np.repeat(off - np.concatenate(([0], np.cumsum(ln)[:-1])), ln) + np.arange(int(ln.sum()))
+        return helpers.sha(o["aligned_text"][idx].tobytes()), helpers.sha(o["aligned_pattern"][idx].tobytes())
+    assert digest(host) == digest(out)
+
+
+@pytest.mark.parametrize("pack", ["1", "0"])
+def test_host_batch_csr_with_nonzero_first_offset(sa, aligner, oracle, monkeypatch, pack):
+    """A CSR batch whose first offsets are not 0 (a view into a larger batch) through the staged host pipeline, packed
+    and unpacked: aln_off must count from the start of the output arenas either way."""
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(9500, seed=31)
+    k = 700
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    monkeypatch.setenv("SA_HOST_PACK", pack)
+    out = aligner.align_batch(1, 23, mat, 5, T, toff[k:], P, poff[k:])
+    N = len(toff) - 1 - k
+    arena = int(toff[-1] - toff[k] + poff[-1] - poff[k])
+    assert int(out["aln_off"].max()) < arena
+    sub = dict(out)
+    assert oracle.check_batch(1, 23, mat, 5, T[toff[k]:], toff[k:] - toff[k], P[poff[k]:], poff[k:] - poff[k], sub) == (0, -1)
+    if pack == "1":
+        assert np.array_equal(out["aln_off"], np.concatenate(([0], np.cumsum(out["results"]["aln_len"])[:-1])).astype(np.uint64))
+    assert N == len(out["results"])
+
+
+def test_residues_outside_the_alphabet_are_refused(sa, aligner):
+    """include/sa_b200.h: a residue >= alphabet_size is SA_ERR_ARGUMENT from the host-buffer entry points."""
+    import synth
+    mat = helpers.matrices()["dna/blast.txt"]
+    t, p = np.array([0, 1, 2, 3, 4], np.uint8), np.array([0, 1, 2], np.uint8)
+    with pytest.raises(sa.SaError):
+        aligner.align(0, 4, mat, 5, t, p)
+    with pytest.raises(sa.SaError):
+        aligner.align(1, 4, mat, 5, p, np.frombuffer(b"ACGT", np.uint8))          # ASCII instead of indices
+    T, toff, P, poff = synth.synthetic_batch(9000, seed=5)
+    bl = helpers.matrices()["protein/blosum62.txt"]
+    for N in (9000, 300):                                                           # staged pipeline and the slot pipeline
+        T2 = T.copy()
+        T2[int(toff[N - 3]) + 7] = 23
+        with pytest.raises(sa.SaError):
+            aligner.align_batch(1, 23, bl, 5, T2, toff[:N + 1], P, poff[:N + 1])
+        aligner.align_batch(1, 23, bl, 5, T, toff[:N + 1], P, poff[:N + 1])         # the context is still usable
+
+
+def test_device_batch_marks_pairs_it_cannot_take(sa, aligner, oracle):
+    """sa_align_batch_device: a pair longer than the caller's max_text_len / max_pattern_len is not aligned and is
+    marked with the sentinel result instead of overrunning the windows sized from those bounds."""
+    import synth
+    T, toff, P, poff = synth.synthetic_batch(600, seed=12, lo=100, hi=200)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    lens_n, lens_m = toff[1:] - toff[:-1], poff[1:] - poff[:-1]
+    cut_n = int(lens_n.max()) - 2          # the longest texts are above the bound
+    out = _device_batch(sa, aligner, 1, mat, T, toff, P, poff, max_n=cut_n, max_m=int(lens_m.max()))
+    over = np.flatnonzero(lens_n > cut_n)
+    assert 1 <= len(over) < 100
+    for i in over:
+        assert int(out["results"]["score"][i]) == -2**31 and int(out["results"]["aln_len"][i]) == 0
+    keep = np.flatnonzero(lens_n <= cut_n).astype(np.uint64)
+    assert oracle.check_batch(1, 23, mat, 5, T, toff, P, poff, out, idx=keep) == (0, -1)

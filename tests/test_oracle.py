@@ -77,3 +77,50 @@ def test_sw_zero_score_wraps_start_indices(oracle):
     a = oracle.align(1, 4, mat, 5, np.zeros(4, np.uint8), np.ones(3, np.uint8))
     assert (a.score, a.aln_len) == (0, 0)
     assert a.start_text == a.start_pattern == 2**64 - 1   # alignSequenceCPU.cpp:13-14,56-57
+
+
+def _oracle_batch_out(oracle, mode, alpha, mat, gap, T, toff, P, poff):
+    """A result set in sa_align_batch's layout, produced by the oracle pair by pair (packed strings)."""
+    N = len(toff) - 1
+    dt = np.dtype([("score", "<i4"), ("_pad", "<i4"), ("aln_len", "<u8"), ("start_text", "<u8"), ("start_pattern", "<u8")])
+    res, aoff = np.zeros(N, dt), np.zeros(N, np.uint64)
+    aT, aP, pos = bytearray(), bytearray(), 0
+    for i in range(N):
+        a = oracle.align(mode, alpha, mat, gap, T[toff[i]:toff[i + 1]], P[poff[i]:poff[i + 1]])
+        res[i] = (a.score, 0, a.aln_len, a.start_text, a.start_pattern)
+        aoff[i] = pos
+        aT += a.aligned_text
+        aP += a.aligned_pattern
+        pos += a.aln_len
+    return dict(results=res, aln_off=aoff, aligned_text=np.frombuffer(bytes(aT) + b"\0", np.uint8).copy(),
+                aligned_pattern=np.frombuffer(bytes(aP) + b"\0", np.uint8).copy())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_batch_checkers_accept_truth_and_catch_corruption(oracle, reference, mode):
+    """oracle.check_batch / reference.check_batch (the multi-threaded checkers behind the GPU batch tests and bench.py's
+    `verified`) agree with the pair-by-pair oracle and flag a single changed field or string byte."""
+    rng = np.random.default_rng(31 + mode)
+    mat = helpers.matrices()["protein/blosum62.txt"]
+    texts, pats = [], []
+    for i in range(60):
+        t, p = helpers.random_case(rng, 23, n_max=120, similar=bool(i % 3))
+        if len(p) > len(t):
+            t, p = p, t
+        texts.append(t)
+        pats.append(p)
+    toff = np.concatenate(([0], np.cumsum([len(t) for t in texts]))).astype(np.int64)
+    poff = np.concatenate(([0], np.cumsum([len(p) for p in pats]))).astype(np.int64)
+    T, P = np.concatenate(texts), np.concatenate(pats)
+    out = _oracle_batch_out(oracle, mode, 23, mat, 5, T, toff, P, poff)
+    for chk in (oracle, reference):
+        assert chk.check_batch(mode, 23, mat, 5, T, toff, P, poff, out, nthreads=3) == (0, -1)
+        assert chk.check_batch(mode, 23, mat, 5, T, toff, P, poff, out, idx=[5, 17, 59], nthreads=2) == (0, -1)
+    bad = dict(out, results=out["results"].copy())
+    bad["results"]["start_pattern"][17] += 1
+    k = int(np.flatnonzero(out["results"]["aln_len"] > 0)[-1])
+    txt = out["aligned_text"].copy()
+    txt[int(out["aln_off"][k])] ^= 1
+    for chk in (oracle, reference):
+        assert chk.check_batch(mode, 23, mat, 5, T, toff, P, poff, bad, nthreads=3) == (1, 17)
+        assert chk.check_batch(mode, 23, mat, 5, T, toff, P, poff, dict(out, aligned_text=txt), nthreads=3) == (1, k)

@@ -257,6 +257,24 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *scoring,
                           uint32_t max_text_len, uint32_t max_pattern_len,
                           void *stream);
 
+/* ---- the multi-GPU dispatcher behind the batch entry (one process, one host thread per device) ----
+ * sa_align_batch over several GPUs of this host: the batch is cut into contiguous cell-balanced ranges
+ * (sa_partition_batch), every device aligns its range from / into the caller's HOST buffers through its own context
+ * and streams, no collective.  The reference hard-codes device 0 (alignSequenceGPU.cu:476).
+ *   options == NULL or n_devices == 0: device 0 only.  Contexts are created on first use and cached per device.
+ * Results are those of sa_align_batch on one device; where a pair's strings land is again reported in aln_off
+ * (every device packs its range behind its own base offset).  Thread-safe (calls are serialised). */
+typedef struct {
+    int32_t n_devices;            /* 1..8 */
+    int32_t devices[8];           /* CUDA device ordinals */
+} sa_options;
+int sa_align_batch_multi(const sa_options *options, const sa_scoring *scoring,
+                         const sa_batch *batch, sa_batch_out *out);
+/* the devices SA_DEVICES names ("0,2,3", or a count "4" = devices 0..3); device 0 when it is unset */
+int sa_options_from_env(sa_options *options);
+/* per-device timing of the last sa_align_batch_multi call: device k of the option list */
+int sa_multi_last_timing(int k, sa_timing *out);
+
 /* ---- multi-GPU helpers ------------------------------------------------------
  * Deterministic cell-balanced split of a batch over `world` ranks (each rank
  * aligns pairs [first[r], first[r+1]) ): no data-path collective is needed. */

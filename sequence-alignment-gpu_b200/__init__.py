@@ -25,7 +25,7 @@ from enum import IntEnum
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsa_b200.so")
+LIB_PATH = os.environ.get("SA_B200_LIB") or os.path.join(_HERE, "libsa_b200.so")      # (SA_B200_LIB: dev aid, A/B builds)
 CSRC = os.path.join(_HERE, "csrc")
 
 

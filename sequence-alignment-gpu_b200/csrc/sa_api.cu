@@ -7,6 +7,7 @@
 #include "sa_batch16.cuh"
 #include "sa_batch16_sw.cuh"
 #include "sa_long.cuh"
+#include "sa_tile_host.h"
 #include "sa_traceback.cuh"
 
 #include <algorithm>
@@ -106,7 +107,7 @@ struct sa_context {
     // column-slice state of sa_strip_fill, consumed by sa_strip_traceback
     struct StripState {
         bool valid = false;
-        int R = 0, CB = 0, alpha = 0;
+        int R = 0, CB = 0, C = 0, alpha = 0;
         uint32_t n_strips = 0;
         size_t strip_stride = 0;
         const uint8_t *d_text = nullptr, *d_pat = nullptr;
@@ -691,6 +692,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
 
 // ------------------------------------------------------------------ long-pair dispatch
 constexpr int LONG_WARPS = 4;
+static_assert(LONG_WARPS == TILE_WARPS, "both long-pair kernels use the same block shape");
 const int kLongR[] = {2, 4, 6, 8, 12, 16};
 
 template <int R>
@@ -758,9 +760,43 @@ int occupancy_long(int R, bool local, size_t smem, bool linked = false, bool wid
 
 struct LongPlan {
     int R, CB, NW, grid;
+    int C;                   // > 0: register-tiled kernel (sa_tile.cuh) with C columns per tile; 0: long_fill_kernel
     uint32_t n_strips, ring;
     size_t strip_stride, row_stride, smem;
 };
+
+// Which long-pair kernel, measured on B200 (tools/probe_tile.py, profiles/README.md round 2).  The register-tiled kernel
+// (sa_tile.cuh) is built for the latency-bound regime -- at most a few strips per SM scheduler, i.e. up to ~300 k rows:
+// 100 000 x 95 217 fills in 10.3 ms with 8 x 2 tiles against 13.7 ms (one-column kernel), 4 000 x 3 800 in 0.41 against
+// 0.61 ms.  With many strips per scheduler (a 125 000-column slice of config 5 has 3 716) the warps hide each other's
+// latencies and the one-column kernel with tall strips issues fewer instructions per cell: 59 ms against 75 ms.
+// SA_TILE="R,C" forces a tile shape; SA_LONG_R or SA_LONG_KERNEL=strip force the one-column kernel (always the path
+// of wide score matrices).
+bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int *R, int *C)
+{
+    (void)n;
+    if (std::getenv("SA_LONG_R")) return false;
+    if (const char *e = std::getenv("SA_LONG_KERNEL")) if (!std::strcmp(e, "strip")) return false;
+    // 8 x 2 tiles fill fastest; when a traceback follows a small matrix, 4 x 4 (strips of 128 rows) keeps the per-strip
+    // passes of the parallel traceback short (3 903 x 3 698: fill + traceback 0.82 ms against 0.99).  Local alignments stay
+    // on the one-column kernel: the per-tile arg-max test costs the tiled sweep its advantage (100 k x 95 k SW: 29.6 ms
+    // tiled, 27.8 ms one-column; both ~2.8x the global fill -- the next thing to fix on this path).
+    int r = 8, c = 2;
+    if (traceback && m <= 16000) { r = 4; c = 4; }
+    bool use = m <= 300000 && !local;
+    if (const char *e = std::getenv("SA_TILE")) {
+        int er = 0, ec = 0;
+        if (std::sscanf(e, "%d,%d", &er, &ec) == 2 && tile_cfg_exists(er, ec)) { r = er; c = ec; use = true; }
+    }
+    *R = r; *C = c;
+    return use;
+}
+
+cudaError_t launch_plan(const LongPlan &P, const LongArgs &A, bool local, int grid, cudaStream_t st, bool wide)
+{
+    if (P.C) return tile_launch(P.R, P.C, local, A.left_col64 || A.right_col64 || A.dbg, A, grid, P.smem, st);
+    return launch_long(P.R, A, local, grid, P.smem, st, wide);
+}
 
 // The kernels carry 4*H in 32 bits: every value the recurrence can produce must fit.  |H| <= max(|S|, gap) * (n + m).
 bool fits_s32(const sa_scoring *sc, uint64_t n, uint64_t m)
@@ -770,7 +806,7 @@ bool fits_s32(const sa_scoring *sc, uint64_t n, uint64_t m)
     return (long double)big * (long double)(n + m + 2) * SCALE < 2147483000.0L;
 }
 
-int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P, bool traceback = true)
+int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P, bool traceback = true, bool linked = false)
 {
     const bool local = sc->mode == SA_LOCAL;
     if (!fits_s32(sc, n, m)) return SA_ERR_SCORE_RANGE;
@@ -789,6 +825,25 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
     }
     const bool wide = ctx->wide;
     if (wide) R = WIDE_R;
+    int tR = 0, tC = 0;
+    P->C = 0;
+    if (!wide && pick_tile(n, m, traceback, local, &tR, &tC)) {
+        P->R = tR; P->C = tC; P->CB = 1; P->NW = tile_nwt(tR, tC);
+        P->n_strips = (uint32_t)((m + 32ull * tR - 1) / (32ull * tR));
+        P->smem = tile_smem_bytes(tR, tC, sc->alphabet_size);
+        const int occ = tile_occupancy(tR, tC, local, linked, P->smem);
+        if (occ < 1) return SA_ERR_LAUNCH;
+        // every strip of a launch should be resident at once when it can be: up to 8 blocks (32 strips) per SM
+        const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 8);
+        const uint64_t needBlocks = (P->n_strips + TILE_WARPS - 1) / TILE_WARPS;
+        P->grid = (int)std::min(maxBlocks, needBlocks);
+        const uint64_t W = (uint64_t)P->grid * TILE_WARPS;
+        P->ring = (uint32_t)std::min<uint64_t>(P->n_strips, W + 1);
+        P->row_stride = (n + 8 + 63) & ~(size_t)63;
+        const size_t nTiles = (n + tC - 1) / tC;
+        P->strip_stride = (nTiles + 31) * 32 * P->NW;
+        return SA_OK;
+    }
     P->R = R; P->CB = cb_for(R); P->NW = R * P->CB / 16;
     P->n_strips = (uint32_t)((m + 32ull * R - 1) / (32ull * R));
     const size_t planes = wide ? 2 : 1;
@@ -818,6 +873,7 @@ int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, u
         T.Lay.dirs = ctx->dirs.as<uint32_t>(); T.Lay.strip_stride = P.strip_stride;
         T.Lay.R = P.R; T.Lay.CB = P.CB; T.Lay.NW = P.NW; T.Lay.ROWS = 32 * P.R;
         T.Lay.cbShift = P.CB == 1 ? 0 : P.CB == 2 ? 1 : P.CB == 4 ? 2 : 3; T.Lay.n = (int)n; T.Lay.m = (int)m;
+        T.Lay.C = P.C; T.Lay.cShift = P.C == 2 ? 1 : P.C == 4 ? 2 : P.C == 8 ? 3 : 0;
         T.text = d_text; T.pattern = d_pat;
         T.S = ctx->dS.as<int32_t>(); T.alpha = alpha; T.gap = gap; T.local = local;
         T.n_strips = P.n_strips;
@@ -915,7 +971,7 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
     SA_TRY(cudaMemsetAsync(A.gmax, 0, 4, st), SA_ERR_LAUNCH);
     cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
-    SA_TRY(launch_long(P.R, A, local, P.grid, P.smem, st, ctx->wide), SA_ERR_LAUNCH);
+    SA_TRY(launch_plan(P, A, local, P.grid, st, ctx->wide), SA_ERR_LAUNCH);
     cudaEventRecord(e1, st);
     cudaEventRecord(e2, st);
     ctx->timing.kernel_launches++;
@@ -927,7 +983,7 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
         T.text = d_text; T.n = (uint32_t)n; T.pattern = d_pat; T.m = (uint32_t)m;
         T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = P.strip_stride;
         T.S = ctx->dS.as<int32_t>(); T.alpha = sc->alphabet_size; T.gap = sc->gap; T.local = local;
-        T.R = P.R; T.CB = P.CB; T.n_strips = P.n_strips;
+        T.R = P.R; T.CB = P.CB; T.C = P.C; T.n_strips = P.n_strips;
         T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
         std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
         T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
@@ -1286,7 +1342,7 @@ int sa_strip_begin(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text,
     const uint32_t stripsTotal = (uint32_t)((m + ROWS - 1) / ROWS);
     SA_TRY(ctx->dirs.reserve((size_t)stripsTotal * P.strip_stride * 4), SA_ERR_MEMORY);
     SA_TRY(ctx->misc.reserve(128), SA_ERR_MEMORY);
-    S.R = P.R; S.CB = P.CB; S.alpha = sc->alphabet_size; S.n_strips = stripsTotal; S.strip_stride = P.strip_stride;
+    S.R = P.R; S.CB = P.CB; S.C = P.C; S.alpha = sc->alphabet_size; S.n_strips = stripsTotal; S.strip_stride = P.strip_stride;
     S.row_stride = P.row_stride; S.smem = P.smem; S.chunk = chunk;
     S.d_text = d_text; S.d_pat = d_pattern; S.n = n; S.m = m; S.col0 = col0; S.total = text_total; S.gap = sc->gap;
     std::memset(S.alphabet, 0, sizeof S.alphabet);
@@ -1370,7 +1426,7 @@ int sa_strip_linked_status(sa_context *ctx, void *stream)
     SA_TRY(cudaMemcpyAsync(&flag, ctx->misc.as<char>() + 56, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream), SA_ERR_COPY);
     SA_TRY(cudaStreamSynchronize((cudaStream_t)stream), SA_ERR_LAUNCH);
     if (const char *path = std::getenv("SA_LONG_DBG")) {
-        std::vector<unsigned long long> h((size_t)ctx->strip.dbg_strips * 4);
+        std::vector<unsigned long long> h((size_t)ctx->strip.dbg_strips * 16);
         if (!h.empty() && cudaMemcpy(h.data(), ctx->tbbuf.p, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
             char name[512];
             std::snprintf(name, sizeof name, "%s.dev%d", path, ctx->device);
@@ -1393,9 +1449,10 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t nStrips = (uint32_t)((rows + ROWS - 1) / ROWS);
-    int occ = occupancy_long(S.R, false, S.smem, d_left64 || d_right64 || std::getenv("SA_LONG_DBG"));
+    const bool linkedKernel = d_left64 || d_right64 || std::getenv("SA_LONG_DBG");
+    int occ = S.C ? tile_occupancy(S.R, S.C, false, linkedKernel, S.smem) : occupancy_long(S.R, false, S.smem, linkedKernel);
     if (occ < 1) return SA_ERR_LAUNCH;
-    const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
+    const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, S.C ? 8 : 2);
     const int grid = (int)std::min<uint64_t>(maxBlocks, (nStrips + LONG_WARPS - 1) / LONG_WARPS);
     const uint32_t ring = (uint32_t)std::min<uint64_t>(nStrips, (uint64_t)grid * LONG_WARPS + 1);
     const size_t rowEntries = (size_t)ring * S.row_stride;
@@ -1419,8 +1476,8 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);
     if (d_left64 || d_right64) SA_TRY(cudaMemsetAsync(A.abort_flag, 0, 4, st), SA_ERR_LAUNCH);
     if (std::getenv("SA_LONG_DBG")) {          // dev aid: per-strip timestamps, dumped by sa_strip_linked_status
-        SA_TRY(ctx->tbbuf.reserve((size_t)nStrips * 32 + 64), SA_ERR_MEMORY);
-        SA_TRY(cudaMemsetAsync(ctx->tbbuf.p, 0, (size_t)nStrips * 32, st), SA_ERR_LAUNCH);
+        SA_TRY(ctx->tbbuf.reserve((size_t)nStrips * 128 + 64), SA_ERR_MEMORY);
+        SA_TRY(cudaMemsetAsync(ctx->tbbuf.p, 0, (size_t)nStrips * 128, st), SA_ERR_LAUNCH);
         A.dbg = ctx->tbbuf.as<unsigned long long>();
         ctx->strip.dbg_strips = nStrips;
     }
@@ -1429,7 +1486,11 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
     cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
-    SA_TRY(launch_long(S.R, A, false, grid, S.smem, st), SA_ERR_LAUNCH);
+    {
+        LongPlan P{};
+        P.R = S.R; P.C = S.C; P.smem = S.smem;
+        SA_TRY(launch_plan(P, A, false, grid, st, false), SA_ERR_LAUNCH);
+    }
     ctx->timing.kernel_launches++;
     if (A.bottom_row) {     // the last strip left its bottom row in its ring row
         const unsigned long long *row = A.rowbuf + (size_t)((nStrips - 1) % ring) * S.row_stride;
@@ -1465,7 +1526,7 @@ int sa_strip_traceback(sa_context *ctx, uint64_t start_row, char *d_outT, char *
         StripTraceArgs T{};
         T.text = S.d_text; T.n = (uint32_t)S.n; T.pattern = S.d_pat; T.m = (uint32_t)S.m;
         T.dirs = ctx->dirs.as<uint32_t>(); T.strip_stride = S.strip_stride;
-        T.alpha = S.alpha; T.R = S.R; T.CB = S.CB; T.col0 = (uint32_t)S.col0; T.start_row = start_row;
+        T.alpha = S.alpha; T.R = S.R; T.CB = S.CB; T.C = S.C; T.col0 = (uint32_t)S.col0; T.start_row = start_row;
         std::memcpy(T.alphabet, S.alphabet, sizeof T.alphabet);
         T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res4;
         strip_traceback_kernel<<<1, 32, 0, st>>>(T);
@@ -1474,7 +1535,7 @@ int sa_strip_traceback(sa_context *ctx, uint64_t start_row, char *d_outT, char *
         return SA_OK;
     }
     LongPlan P{};
-    P.R = S.R; P.CB = S.CB; P.NW = S.R * S.CB / 16; P.n_strips = S.n_strips; P.strip_stride = S.strip_stride;
+    P.R = S.R; P.CB = S.CB; P.C = S.C; P.NW = S.C ? tile_nwt(S.R, S.C) : S.R * S.CB / 16; P.n_strips = S.n_strips; P.strip_stride = S.strip_stride;
     return enqueue_parallel_traceback(ctx, P, S.n, S.m, S.d_text, S.d_pat, S.alpha, S.gap, S.alphabet, false, nullptr, nullptr,
                                       nullptr, nullptr, d_outT, d_outP, cap, d_res4, true, (long long)start_row, S.col0 > 0,
                                       (double)S.total / (double)S.m, st);
@@ -1875,6 +1936,103 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
     tm.d2h_bytes = d2hBytes;
     ctx->timing = tm;
     ctx->timing_dirty = false;
+    return SA_OK;
+}
+
+// --------------------------------------------------------------- multi-GPU dispatcher (one process)
+namespace {
+std::mutex g_multi_mu;
+sa_context *g_multi_ctx[64] = {};
+sa_timing g_multi_timing[8] = {};
+}
+
+int sa_options_from_env(sa_options *o)
+{
+    if (!o) return SA_ERR_ARGUMENT;
+    std::memset(o, 0, sizeof *o);
+    o->n_devices = 1;
+    const char *e = std::getenv("SA_DEVICES");
+    if (!e || !*e) return SA_OK;
+    std::vector<int> v;
+    for (const char *q = e; *q;) {
+        char *end = nullptr;
+        const long d = std::strtol(q, &end, 10);
+        if (end == q) return SA_ERR_ARGUMENT;
+        v.push_back((int)d);
+        q = end;
+        if (*q == ',') ++q; else if (*q) return SA_ERR_ARGUMENT;
+    }
+    if (v.size() == 1 && std::strchr(e, ',') == nullptr && v[0] >= 1) {          // a count
+        const int cnt = v[0];
+        v.clear();
+        for (int d = 0; d < cnt; ++d) v.push_back(d);
+    }
+    if (v.empty() || v.size() > 8) return SA_ERR_ARGUMENT;
+    o->n_devices = (int32_t)v.size();
+    for (size_t k = 0; k < v.size(); ++k) o->devices[k] = v[k];
+    return SA_OK;
+}
+
+int sa_multi_last_timing(int k, sa_timing *out)
+{
+    if (k < 0 || k >= 8 || !out) return SA_ERR_ARGUMENT;
+    std::lock_guard<std::mutex> g(g_multi_mu);
+    *out = g_multi_timing[k];
+    return SA_OK;
+}
+
+int sa_align_batch_multi(const sa_options *opt, const sa_scoring *sc, const sa_batch *b, sa_batch_out *out)
+{
+    if (!sc || !b || !out || !b->text_off || !b->pattern_off || !out->results || !out->aln_off) return SA_ERR_ARGUMENT;
+    sa_options one{};
+    one.n_devices = 1;
+    if (!opt || opt->n_devices == 0) opt = &one;
+    const int D = opt->n_devices;
+    if (D < 1 || D > 8) return SA_ERR_ARGUMENT;
+    const int have = sa_device_count();
+    if (have < 1) return SA_ERR_NO_DEVICE;
+    for (int k = 0; k < D; ++k) {
+        if (opt->devices[k] < 0 || opt->devices[k] >= have || opt->devices[k] >= 64) return SA_ERR_NO_DEVICE;
+        for (int j = 0; j < k; ++j) if (opt->devices[j] == opt->devices[k]) return SA_ERR_ARGUMENT;
+    }
+    const uint64_t N = b->n_pairs;
+    if (N == 0) return SA_OK;
+    std::lock_guard<std::mutex> g(g_multi_mu);
+    for (int k = 0; k < D; ++k) {
+        sa_context *&c = g_multi_ctx[opt->devices[k]];
+        if (!c) { const int rc = sa_create(opt->devices[k], &c); if (rc) { c = nullptr; return rc; } }
+    }
+    const int64_t *to = b->text_off, *po = b->pattern_off;
+    if ((uint64_t)(to[N] - to[0] + po[N] - po[0]) > out->arena_capacity) return SA_ERR_CAPACITY;
+    std::vector<uint64_t> first((size_t)D + 1);
+    int rc = sa_partition_batch(to, po, N, D, first.data());
+    if (rc) return rc;
+    std::vector<int> status((size_t)D, SA_OK);
+    auto work = [&](int k) {
+        const uint64_t f = first[k], cnt = first[k + 1] - f;
+        g_multi_timing[k] = sa_timing{};
+        if (cnt == 0) return;
+        // the device's range as a batch of its own: offsets stay absolute (sa_align_batch rebases), the output arenas
+        // start at the range's own slot base, and aln_off comes back relative to that base
+        const uint64_t base = (uint64_t)(to[f] - to[0]) + (uint64_t)(po[f] - po[0]);
+        sa_batch sb{cnt, b->text, to + f, b->pattern, po + f};
+        sa_batch_out so{out->results + f, out->aln_off + f, out->aligned_text + base, out->aligned_pattern + base,
+                        (uint64_t)(to[f + cnt] - to[f]) + (uint64_t)(po[f + cnt] - po[f])};
+        sa_context *c = g_multi_ctx[opt->devices[k]];
+        status[k] = sa_align_batch(c, sc, &sb, &so);
+        if (status[k] == SA_OK) {
+            if (base) for (uint64_t p = 0; p < cnt; ++p) so.aln_off[p] += base;
+            sa_last_timing(c, &g_multi_timing[k]);
+        }
+    };
+    if (D == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 1; k < D; ++k) th.emplace_back(work, k);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < D; ++k) if (status[k] != SA_OK) return status[k];
     return SA_OK;
 }
 

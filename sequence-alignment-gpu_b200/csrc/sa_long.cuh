@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(WARPS * 32) long_fill_kernel(const LongArgs A)
 }
 
 // bottom row of a row chunk: the last strip wrote it into its ring row as {4H, tag} words
-__global__ void long_bottom_row_kernel(const unsigned long long *row, int *bottom_row, const uint32_t n)
+static __global__ void long_bottom_row_kernel(const unsigned long long *row, int *bottom_row, const uint32_t n)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) bottom_row[j] = (int)(uint32_t)row[j];
@@ -374,6 +374,7 @@ struct LongTraceArgs {
     const uint32_t *dirs;    uint64_t strip_stride;
     const int32_t *S;  int alpha, gap, local;
     int R, CB;
+    int C;                   // > 0: tile layout of sa_tile.cuh with C columns per tile (then CB is unused)
     uint32_t n_strips;
     const int *cand_v; const uint32_t *cand_i; const uint32_t *cand_j;
     int32_t *score;          // in (NW) / out (SW)
@@ -384,7 +385,7 @@ struct LongTraceArgs {
     int emit;                // 0: score / arg-max only (the reference's BENCHMARK mode)
 };
 
-__global__ void long_traceback_kernel(const LongTraceArgs A)
+static __global__ void long_traceback_kernel(const LongTraceArgs A)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int NW = A.R * A.CB / 16;
@@ -413,10 +414,17 @@ __global__ void long_traceback_kernel(const LongTraceArgs A)
     auto fetch = [&](int ii, int jj) -> int {
         const int s = (ii - 1) / ROWS, rr = (ii - 1) % ROWS;
         const int ll = rr / A.R, r = rr % A.R;
-        const int k = (jj - 1) + ll;
-        const int kb = k / A.CB, kk = k % A.CB;
-        const int bit = (kk * A.R + r) * 2;
-        const size_t addr = (size_t)s * A.strip_stride + (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        int bit; size_t addr;
+        if (A.C) {
+            const int k = (jj - 1) / A.C + ll, cc = (jj - 1) % A.C;
+            bit = (cc * A.R + r) * 2;
+            addr = (size_t)s * A.strip_stride + ((size_t)k * 32 + ll) * (A.R * A.C / 16) + (bit >> 5);
+        } else {
+            const int k = (jj - 1) + ll;
+            const int kb = k / A.CB, kk = k % A.CB;
+            bit = (kk * A.R + r) * 2;
+            addr = (size_t)s * A.strip_stride + (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        }
         if (addr != cachedAddr) { cachedAddr = addr; cachedWord = A.dirs[addr]; }
         return (cachedWord >> (bit & 31)) & 3;
     };
@@ -468,6 +476,7 @@ struct StripTraceArgs {
     const uint32_t *dirs;    uint64_t strip_stride;
     int alpha;
     int R, CB;
+    int C;                   // > 0: tile layout (see LongTraceArgs)
     uint32_t col0;
     uint64_t start_row;
     char alphabet[MAX_ALPHA + 1];
@@ -476,7 +485,7 @@ struct StripTraceArgs {
     uint64_t *res;           // [0]=len of the piece  [1]=row where the path leaves the slice  [2],[3]= text/pattern index state
 };
 
-__global__ void strip_traceback_kernel(const StripTraceArgs A)
+static __global__ void strip_traceback_kernel(const StripTraceArgs A)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int NW = A.R * A.CB / 16;
@@ -490,10 +499,17 @@ __global__ void strip_traceback_kernel(const StripTraceArgs A)
     auto fetch = [&](int ii, int jj) -> int {
         const int s = (ii - 1) / ROWS, rr = (ii - 1) % ROWS;
         const int ll = rr / A.R, r = rr % A.R;
-        const int k = (jj - 1) + ll;
-        const int kb = k / A.CB, kk = k % A.CB;
-        const int bit = (kk * A.R + r) * 2;
-        const size_t addr = (size_t)s * A.strip_stride + (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        int bit; size_t addr;
+        if (A.C) {
+            const int k = (jj - 1) / A.C + ll, cc = (jj - 1) % A.C;
+            bit = (cc * A.R + r) * 2;
+            addr = (size_t)s * A.strip_stride + ((size_t)k * 32 + ll) * (A.R * A.C / 16) + (bit >> 5);
+        } else {
+            const int k = (jj - 1) + ll;
+            const int kb = k / A.CB, kk = k % A.CB;
+            bit = (kk * A.R + r) * 2;
+            addr = (size_t)s * A.strip_stride + (size_t)(kb * NW + (bit >> 5)) * 32 + ll;
+        }
         if (addr != cachedAddr) { cachedAddr = addr; cachedWord = A.dirs[addr]; }
         return (cachedWord >> (bit & 31)) & 3;
     };

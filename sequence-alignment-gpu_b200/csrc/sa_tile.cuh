@@ -1,0 +1,606 @@
+// sa_tile.cuh -- one long pair, register-tiled (BASELINE configs 1-3 and each GPU's column slice of config 5).
+//
+// Replaces long_fill_kernel (sa_long.cuh) for every score matrix that fits the one-byte profile.  Same strip chain --
+// the (m+1) x (n+1) matrix is cut into horizontal strips of 32*R rows, one warp per strip, lane l owns R rows, all
+// strips form one systolic chain through {4H, tag} words in L2 -- but a lane now advances by a TILE of R rows x C
+// columns per "macro-step" instead of one column:
+//
+//   * the R*C cells of a tile are independent along its anti-diagonals, so ONE warp has enough instruction-level
+//     parallelism to keep its scheduler issuing (the one-column step was a serial chain of R cells: 3 cycles per
+//     instruction, 6 % of the warp slots active -- profiles/r01_long_c3_ncu.txt);
+//   * the per-step bookkeeping (neighbour exchange, text / profile / top-row fetch, boundary store, direction store,
+//     loop control) is paid once per R*C cells: C shuffles, C profile loads, one direction store of R*C/16 words;
+//   * the bottom value of column cc is handed to the lane below as soon as that column is done (the shuffle of
+//     column 0 overlaps the sweep of columns 1..C-1), so the exchange latency is off the critical path;
+//   * lane 31 publishes the strip's bottom row with 128-bit stores (two {4H, tag} words each), the strip below fetches
+//     it with 128-bit loads, TG macro-steps (TG*C columns) ahead of use.
+//
+// Cell arithmetic, tie-breaking and the 2-bit tags are those of sa_cell.cuh ("tagged max"); results are bit-identical
+// to long_fill_kernel and to the reference's alignSequenceCPU.cpp (tests/test_gpu_parity.py).
+//
+// Direction words ("tile layout"): word(s, k, lane, w) at  s*strip_stride + (k*32 + lane)*NWT + w,  k = macro-step =
+// tile index + lane, NWT = R*C/16; cell (r, cc) of the tile sits at bit (cc*R + r)*2 of the lane's NWT words.  One
+// 4/8/16-byte store per lane and macro-step, 128..512 contiguous bytes per warp; 0.25 B/cell.
+//
+// SW arg-max (first maximum in row-major order, alignSequenceCPU.cpp:191-192): every tile reduces to its maximum with
+// a VIMNMX3 tree; only when that maximum can still be the alignment-wide arg-max (>= the lane's best and >= the
+// running global maximum) the warp takes a slow path that recomputes the tile to locate the cell.
+#pragma once
+#include "sa_tile_host.h"
+
+namespace sa {
+
+#ifndef SA_TILE_TG
+#define SA_TILE_TG 8
+#endif
+#ifndef SA_TILE_SLEEP
+#define SA_TILE_SLEEP 20
+#endif
+constexpr int TG = SA_TILE_TG;     // macro-steps per top-row group (prefetch distance of the strip hand-off)
+#ifndef SA_TILE_TG_REQ
+#define SA_TILE_TG_REQ 3
+#endif
+constexpr int TG_REQ = SA_TILE_TG_REQ;   // macro-step of a group after which the next group is requested
+constexpr int TEXT_RING = 128;     // tiles of text kept in shared memory per warp
+
+__host__ __device__ constexpr size_t tile_warp_smem(int R, int C, int alpha)
+{
+    // profile, text ring, top-row window (2*TG tiles), exchange buffer (C/2 parts of 32 x 2 ints)
+    return ((size_t)alpha * 32 * rpad_for(R) + (size_t)TEXT_RING * C + (size_t)2 * TG * C * 4 + (size_t)(C / 2) * 256 + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void ld_volatile_v2u64(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// C bottom values of lane 31 as {4H, tag} words, two per 128-bit store, under ONE predicate (flag != 0) instead of a branch
+template <int C>
+__device__ __forceinline__ void st_row_words_if(const uint32_t flag, unsigned long long *p, const int (&v)[C], const uint32_t tagHi)
+{
+    if (C == 2)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.volatile.global.v4.u32 [%1], {%2, %4, %3, %4};\n\t}"
+                     ::"r"(flag), "l"(p), "r"(v[0]), "r"(v[1 % C]), "r"(tagHi) : "memory");
+    else {
+#pragma unroll
+        for (int cc = 0; cc < C; cc += 4)
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.volatile.global.v4.u32 [%1], {%2, %6, %3, %6};\n\t"
+                         "@q st.volatile.global.v4.u32 [%1+16], {%4, %6, %5, %6};\n\t}"
+                         ::"r"(flag), "l"(p + cc), "r"(v[cc]), "r"(v[(cc + 1) % C]), "r"(v[(cc + 2) % C]), "r"(v[(cc + 3) % C]), "r"(tagHi) : "memory");
+    }
+}
+
+// Slow path of the SW arg-max: recompute one tile (plain cells, no tags) and return r*C + cc of the row-major first
+// cell (within the tile's first ncols columns) whose value equals v (R*C when there is none).
+template <int R, int C>
+__device__ __noinline__ int tile_locate(const int v, const int KL, const int KT, const int corner,
+                                        const int (&cin)[R], const int (&top)[C], const uint32_t (&pw)[C][(R + 3) / 4], const int ncols)
+{
+    int c[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[r] = cin[r];
+    int key = R * C;
+    int d0 = corner;
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) {
+        int t = top[cc], d = d0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int x = __dp4a((int)pw[cc][r >> 2], onehot(r), d);
+            const int cn = viaddmax_relu(t, KT, viaddmax(c[r], KL, x)) & ~3;
+            d = c[r]; t = cn; c[r] = cn;
+            if (cn == v && cc < ncols) key = min(key, r * C + cc);
+        }
+        d0 = top[cc];
+    }
+    return key;
+}
+
+template <int R, int C, bool LOCAL, int WARPS, bool LINKED = false>
+__global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
+{
+    static_assert((R * C) % 16 == 0, "a tile must fill whole direction words");
+    static_assert(C == 2 || C == 4 || C == 8, "tile width");
+    constexpr int NWT = tile_nwt(R, C);
+    static_assert(NWT == 1 || NWT == 2 || NWT == 4, "direction words per lane and macro-step: one vector store");
+    constexpr int RPAD = rpad_for(R);
+    constexpr int PS = 32 * RPAD;
+    constexpr int NPW = (R + 3) / 4;
+    constexpr int ROWS = 32 * R;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int alpha = A.alpha;
+    int8_t *S4s = reinterpret_cast<int8_t *>(smem);
+    unsigned char *wbase = smem + 32 * MAX_ALPHA + (size_t)warp * tile_warp_smem(R, C, alpha);
+    unsigned char *profS = wbase;
+    unsigned char *textRing = profS + alpha * PS;
+    int *topWin = reinterpret_cast<int *>(textRing + TEXT_RING * C);
+    int *xbuf = topWin + 2 * TG * C;
+    for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
+    __syncthreads();
+    const unsigned char *profL = profS + lane * RPAD;       // this lane's R profile bytes of letter 0
+
+    const int KL = 2 - SCALE * A.gap, KT = 1 - SCALE * A.gap;
+    const uint32_t W = gridDim.x * WARPS;
+    const int n = (int)A.n, m = (int)A.m;
+    const int nTiles = (n + C - 1) / C;          // tiles per lane
+    const int nFull = n / C;                     // tiles that lie completely inside the text
+    const int kEnd = nTiles + 31;                // macro-steps of a strip
+
+    for (uint32_t s = blockIdx.x * WARPS + warp; s < A.n_strips; s += W) {
+        const int row0 = (int)s * ROWS;                 // pattern index of the strip's first row
+        // ---- query profile of this strip: prof[a][lane*RPAD + r] = 4*S[p_row][a], padding rows -128 ----
+        __syncwarp();
+        for (int i = lane; i < ROWS; i += 32) {
+            const int off = (i / R) * RPAD + (i % R);
+            const int gi = row0 + i;
+            if (gi < m) {
+                const int8_t *srow = S4s + 32 * min((int)A.pattern[gi], alpha - 1);
+                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)srow[a];
+            } else {
+                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)0x80;
+            }
+        }
+        // ---- text ring: tiles 0..63 now, 64..95 in flight ----
+        auto load_tile_letters = [&](const int tile) -> unsigned long long {
+            unsigned long long w = 0;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {
+                const int j = tile * C + cc;
+                const unsigned letter = j < n ? (unsigned)min((int)A.text[j], alpha - 1) : 0u;
+                w |= (unsigned long long)letter << (8 * cc);
+            }
+            return w;
+        };
+        auto store_tile_letters = [&](const int tile, const unsigned long long w) {
+            unsigned char *p = textRing + (tile & (TEXT_RING - 1)) * C;
+            if (C == 2) *reinterpret_cast<unsigned short *>(p) = (unsigned short)w;
+            else if (C == 4) *reinterpret_cast<uint32_t *>(p) = (uint32_t)w;
+            else *reinterpret_cast<unsigned long long *>(p) = w;
+        };
+        store_tile_letters(lane, load_tile_letters(lane));
+        store_tile_letters(32 + lane, load_tile_letters(32 + lane));
+        store_tile_letters(64 + lane, 0ull);
+        store_tile_letters(96 + lane, 0ull);            // tiles -32..-1 of the ramp read these slots
+        unsigned long long tnext = load_tile_letters(64 + lane);
+        __syncwarp();
+
+        // ---- boundary state (left border of the slice) ----
+        auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+        if (LINKED && A.dbg && lane == 0) A.dbg[3 * s] = gtime();
+        // linked slices: wait (warp-uniformly, see sa_long.cuh) until the left neighbour's kernel has delivered the word
+        auto linked_border = [&](const int gi) -> int {
+            const bool need = gi > 0 && gi <= m;
+            unsigned long long v = need ? ld_volatile_u64(A.left_col64 + gi) : 0ull;
+            const long long t0 = clock64();
+            for (unsigned it = 1;; ++it) {
+                const bool ok = !need || (uint32_t)(v >> 32) == A.xtag;
+                if (__all_sync(0xffffffffu, ok)) break;
+                if ((it & 1023u) == 0) {
+                    bool dead = *reinterpret_cast<volatile int *>(A.abort_flag) != 0;
+                    if (clock64() - t0 > 20000000000ll) { atomicExch(A.abort_flag, 1); dead = true; }     // ~10 s: the neighbour is gone
+                    if (__any_sync(0xffffffffu, dead)) break;
+                }
+                __nanosleep(1000);
+                if (!ok) v = ld_volatile_u64(A.left_col64 + gi);
+            }
+            return gi == 0 ? (LOCAL ? 0 : -SCALE * A.gap * (int)A.col0) : (int)(uint32_t)v;
+        };
+        int c[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gi = row0 + lane * R + r + 1;     // DP row
+            if (LINKED && A.left_col64) c[r] = linked_border(gi);
+            else if (A.left_col) c[r] = gi <= m ? A.left_col[gi] : 0;
+            else c[r] = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
+        }
+        int corner;                                     // 4*H(i0-1, column before the tile)
+        {
+            const int gi = row0 + lane * R;
+            if (LINKED && A.left_col64) corner = linked_border(gi);
+            else if (A.left_col) corner = gi <= m ? A.left_col[gi] : 0;
+            else corner = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
+        }
+        if (LINKED && A.dbg) { __syncwarp(); if (lane == 0) A.dbg[3 * s + 1] = gtime(); }
+
+        int bestv = 0, besti = 0, bestj = 0;
+        int gmCached = 0;                               // lane-local copy of *A.gmax (a lower bound)
+        const bool rowsValid = row0 + lane * R < m;
+        const bool hasUp = s > 0, hasDown = s + 1 < A.n_strips;
+        // lane 31 publishes the strip's bottom row for the strip below -- or, for the last strip of a row chunk, for
+        // long_bottom_row_kernel, which copies it out of the ring
+        const bool writesRow = lane == 31 && (hasDown || A.bottom_row != nullptr);
+        const uint32_t writesFlag = writesRow ? 1u : 0u;
+        const unsigned long long *rowIn = A.rowbuf + (size_t)((s + A.ring - 1) % A.ring) * A.row_stride;
+        unsigned long long *rowOut = A.rowbuf + (size_t)(s % A.ring) * A.row_stride;
+        const uint32_t wantTag = A.tag_base | s;          // producer s-1 writes (s-1)+1
+        const unsigned long long myTagHi = (unsigned long long)(A.tag_base | (s + 1)) << 32;
+        uint32_t *dbase = A.dirs + (size_t)s * A.strip_stride + lane * NWT;
+
+        // ---- top row of the strip: groups of TG tiles, fetched one group ahead by lanes 0..TG-1 into a window of 2*TG
+        // tiles (lane 0 reads tile k+1 while macro-step k runs, so a group must survive the arrival of the next one) ----
+        unsigned long long pend[C];
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) pend[cc] = 0;
+        unsigned long long dbgSpins = 0, dbgSpinNs = 0, dbgStalls = 0, dbgRampStalls = 0, dbgEnter = 0, dbgExit = 0, dbgWrite = 0;      // (LINKED + dbg only)
+        // group with first tile `first`: lanes q < TG own tile first + q (window slot (first + q) % (2*TG))
+        auto request_top = [&](const int first) {
+            const int col = (first + lane) * C;
+            if (lane < TG && col >= 0 && col < n) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc += 2) ld_volatile_v2u64(rowIn + col + cc, pend[cc], pend[cc + 1]);
+            }
+        };
+        auto top_upkeep = [&](const int first) {
+            const int col = (first + lane) * C;
+            int tv[C];
+            if (hasUp) {
+                const bool mine = lane < TG && col >= 0 && col < n;
+                const unsigned long long tSpin = (LINKED && A.dbg) ? gtime() : 0ull;
+                bool spun = false;
+                if (LINKED && A.dbg && first == 8001) dbgEnter = tSpin;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) ok = ok && (!(mine && col + cc < n) || (uint32_t)(pend[cc] >> 32) == wantTag);
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (LINKED && A.dbg) { spun = true; ++dbgSpins; }
+                    if (!ok) {
+                        if (SA_TILE_SLEEP > 0) __nanosleep(SA_TILE_SLEEP);
+#pragma unroll
+                        for (int cc = 0; cc < C; cc += 2) ld_volatile_v2u64(rowIn + col + cc, pend[cc], pend[cc + 1]);
+                    }
+                }
+                if (LINKED && A.dbg && spun) { dbgSpinNs += gtime() - tSpin; ++dbgStalls; if (first <= 33) ++dbgRampStalls; }
+                if (LINKED && A.dbg && first == 8001) dbgExit = gtime();
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) tv[cc] = (int)(uint32_t)pend[cc];
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc)
+                    tv[cc] = A.top_row ? (col >= 0 && col + cc < n ? A.top_row[col + cc] : 0) : LOCAL ? 0 : -SCALE * A.gap * (col + cc + 1 + (int)A.col0);
+            }
+            if (lane < TG) {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) topWin[((first + lane) & (2 * TG - 1)) * C + cc] = tv[cc];
+            }
+            __syncwarp();
+            // The next group is NOT requested here but in the middle of this one (TG_REQ macro-steps later): requested
+            // right away, the words of a producer that is only ~40 tiles ahead are not written yet, the reload at the
+            // next group boundary costs an L2 round trip, and the lag a strip picks up that way while it starts stays
+            // with it for the whole sweep (both run at the same speed) -- times the number of strips in the chain.
+        };
+        // text ring upkeep, every 32 macro-steps: tiles k+32..k+63 become readable, k+64..k+95 are requested
+        auto text_upkeep = [&](const int k) {
+            store_tile_letters(k + 32 + lane, tnext);
+            tnext = load_tile_letters(k + 64 + lane);
+            if (LOCAL) gmCached = max(gmCached, *reinterpret_cast<volatile int *>(A.gmax));
+            __syncwarp();
+        };
+
+        // ---- neighbour exchange through shared memory ----
+        // Lane l leaves the bottom values of its tile in xbuf, two columns ("part") per 64-bit store, as soon as the
+        // second column of the part is done; lane l+1 picks them up for its next macro-step.  Lane 0 reads the top-row
+        // window instead -- the same code with another address -- so there is no shuffle, no lane-0 select, and the
+        // exchange latency hides behind the rest of the tile: the parts 0..NP-2 of the next macro-step are loaded just
+        // before the last cell of this one, the last part right at its start (it is needed C-2 diagonals later).
+        // (Shuffles could not be placed: ptxas gathers them at the end of the macro-step, where each one stalls the
+        // first cells of the next tile -- profiles/r02_tile44_ncu.txt.)  All accesses are volatile: they stay in
+        // program order, and the lanes of the warp run in lock-step through the straight-line modes.
+        constexpr int NP = C / 2;
+        const uint32_t sX = (uint32_t)__cvta_generic_to_shared(xbuf);
+        const uint32_t wrBase = sX + lane * 8;                                          // part p at + p*256
+        const uint32_t rdBase = lane ? sX + (lane - 1) * 8 : (uint32_t)__cvta_generic_to_shared(topWin);
+        const uint32_t rdPart = lane ? 256u : 8u;                                       // bytes between parts
+        const uint32_t rdTile = lane ? 0u : (uint32_t)(C * 4);                          // bytes between tiles (lane 0 only)
+        auto read_part = [&](const int tile, const int p, int &a, int &b) {
+            const uint32_t addr = rdBase + p * rdPart + (uint32_t)(tile & (2 * TG - 1)) * rdTile;
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+        };
+        auto write_part = [&](const int p, const int a, const int b) {
+            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(wrBase + p * 256), "r"(a), "r"(b) : "memory");
+        };
+
+        // Lane 0 reads the top values of tile k+1 during macro-step k, so the groups are tiles 8g+1 .. 8g+8 and tile 0
+        // comes first
+        if (hasUp) request_top(1 - TG);
+        top_upkeep(1 - TG);
+        if (hasUp) request_top(1);
+        // profile words of the macro-step about to run (prefetched one macro-step ahead), text word of the one after
+        uint32_t pw[C][NPW];
+        auto text_word = [&](const int kb) -> unsigned long long {
+            const unsigned char *p = textRing + ((kb & (TEXT_RING - 1)) * C);
+            if (C == 2) return *reinterpret_cast<const unsigned short *>(p);
+            if (C == 4) return *reinterpret_cast<const uint32_t *>(p);
+            return *reinterpret_cast<const unsigned long long *>(p);
+        };
+        auto load_profile = [&](const unsigned long long tw, uint32_t (&dst)[C][NPW]) {
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {
+                const uint32_t letter = (uint32_t)(tw >> (8 * cc)) & 0xffu;
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(profL + letter * PS);
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) dst[cc][q] = p[q];
+            }
+        };
+        load_profile(text_word(0 - lane), pw);
+        unsigned long long twN = text_word(1 - lane);
+        int top[C];                                     // values above the lane's first row for the coming macro-step
+#pragma unroll
+        for (int p = 0; p < NP; ++p) read_part(0, p, top[2 * p], top[2 * p + 1]);      // (lanes > 0: not used before their ramp ends)
+
+        // Ramp-up: a lane whose first tile has not arrived yet computes on (its tile index is negative, nothing it writes is
+        // ever read) and takes its real border state when its tile 0 starts -- so the ramp runs the same straight-line
+        // code as the steady state.  The ramp is on the critical path of the whole strip chain: strip s+1 starts once
+        // strip s has produced its first columns.
+        int cb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cb[r] = c[r];
+        const int cornerB = corner;
+        unsigned long long *rowW = rowOut - (long long)lane * C;          // where lane 31 stores tile k - lane of macro-step k
+        uint32_t *dirW = dbase;
+
+        // Drain: the mirror image.  A lane that has finished its last tile computes on (tiles past the text, never read)
+        // after parking its final column in cfin; the columns of the last, partial tile that lie past the text pass their
+        // left value through.  The drain is on the critical path as well: every strip ends 32 macro-steps after the one
+        // above it, so a slow drain (the generic mode cost 2.5x a steady macro-step) delays the end of the whole chain by
+        // that much per strip (profiles/README.md, round 2).
+        int cfin[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cfin[r] = c[r];
+
+        // One macro-step.  MODE 1 = steady state (every lane has a full tile), MODE 2 = ramp-up, MODE 3 = drain (see above),
+        // MODE 0 = generic (all bounds checked, divergent: texts too short for the straight-line modes).
+        auto macro_step = [&](const int k, auto modeTag) {
+            constexpr int MODE = decltype(modeTag)::value;
+            const int kb = k - lane;
+            if (MODE == 2 && kb == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) c[r] = cb[r];
+                corner = cornerB;
+            }
+            // prefetch for the next macro-step: its profile words, and the text word of the one after
+            uint32_t pwN[C][NPW];
+            load_profile(twN, pwN);
+            twN = text_word(kb + 2);
+            if (MODE == 0) {
+#pragma unroll
+                for (int p = 0; p < NP; ++p) read_part(k, p, top[2 * p], top[2 * p + 1]);
+            } else read_part(k, NP - 1, top[C - 2], top[C - 1]);
+            const bool active = MODE == 1 || (MODE == 2 ? kb >= 0 : MODE == 3 ? kb < nTiles : (kb >= 0 && kb < nTiles));
+            // valid columns of the tile (drain: the tile after the last full one is partial, or empty when C divides n)
+            const int ncols = (MODE == 1 || MODE == 2) ? C : MODE == 3 ? (kb == nFull ? n - nFull * C : C) : min(C, n - kb * C);
+            int cin[R], topIn[C];
+#pragma unroll
+            for (int r = 0; r < R; ++r) cin[r] = c[r];
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) topIn[cc] = top[cc];
+            const int cornerIn = corner;
+            // tags of the tile: one partial word per column, so that the deposits do not form one long dependency chain
+            uint32_t accp[C][NWT];
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                for (int w = 0; w < NWT; ++w) accp[cc][w] = 0;
+            int bot[C];
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) bot[cc] = c[R - 1];
+            int tmax = 0;
+            if (MODE != 0) {
+                // Straight-line modes: the cells in ANTI-DIAGONAL order (d = r + cc).  The cells of one diagonal are
+                // independent, so consecutive instructions of the stream do not wait for each other: a lone warp per
+                // scheduler is the normal case of this kernel (column order left ~1 stall cycle per instruction,
+                // profiles/r02_tile44_ncu.txt).
+                int v[R][C];
+#pragma unroll
+                for (int d = 0; d < R + C - 1; ++d) {
+                    if (d == R + C - 2) {          // before the last cell: the early parts of the next macro-step's top values
+#pragma unroll
+                        for (int p = 0; p + 1 < NP; ++p) read_part(k + 1, p, top[2 * p], top[2 * p + 1]);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        const int r = d - cc;
+                        if (r < 0 || r >= R) continue;
+                        const int left = cc ? v[r][cc ? cc - 1 : 0] : c[r];
+                        const int tp = r ? v[r ? r - 1 : 0][cc] : topIn[cc];
+                        const int dg = (r && cc) ? v[r ? r - 1 : 0][cc ? cc - 1 : 0] : r ? c[r ? r - 1 : 0] : cc ? topIn[cc ? cc - 1 : 0] : corner;
+                        const int x = __dp4a((int)pw[cc][r >> 2], onehot(r), dg);         // cD = 4*(D + s)
+                        const int mx = viaddmax(left, KL, x);                             // max(cL, cD)
+                        const int h = LOCAL ? viaddmax_relu(tp, KT, mx) : viaddmax(tp, KT, mx);
+                        const int cn = h & ~3;
+                        const int bit = 2 * (cc * R + r);
+                        deposit_tag(accp[cc][bit >> 5], h, cn, bit & 31);
+                        const int cv = (MODE == 3 && cc >= ncols) ? left : cn;             // drain: past the text, keep the last column
+                        v[r][cc] = cv;
+                        if (r == R - 1) {
+                            bot[cc] = cv;
+                            if (cc & 1) write_part(cc >> 1, bot[cc - 1 >= 0 ? cc - 1 : 0], cv);      // hand-off as soon as the part exists
+                        }
+                    }
+                }
+                corner = topIn[C - 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r) c[r] = v[r][C - 1];
+                if (MODE == 3) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cfin[r] = (kb == nTiles - 1) ? c[r] : cfin[r];
+                }
+                if (LOCAL) {
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        int w = v[0][cc];
+#pragma unroll
+                        for (int r = 1; r < R; r += 2) w = (r + 1 < R) ? __vimax3_s32(w, v[r][cc], v[r + 1 < R ? r + 1 : r][cc]) : max(w, v[r][cc]);
+                        tmax = max(tmax, w);
+                    }
+                }
+            } else {
+                if (active) {
+                    int d0 = corner;
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        if (cc < ncols) {
+                            int t = topIn[cc], d = d0;
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const int x = __dp4a((int)pw[cc][r >> 2], onehot(r), d);
+                                const int mx = viaddmax(c[r], KL, x);
+                                const int h = LOCAL ? viaddmax_relu(t, KT, mx) : viaddmax(t, KT, mx);
+                                const int cn = h & ~3;
+                                const int bit = 2 * (cc * R + r);
+                                deposit_tag(accp[cc][bit >> 5], h, cn, bit & 31);
+                                d = c[r]; t = cn; c[r] = cn;
+                            }
+                            d0 = topIn[cc];
+                            corner = topIn[cc];
+                            if (LOCAL) {
+                                int w = c[0];
+#pragma unroll
+                                for (int r = 1; r < R; r += 2) w = (r + 1 < R) ? __vimax3_s32(w, c[r], c[r + 1 < R ? r + 1 : r]) : max(w, c[r]);
+                                tmax = max(tmax, w);
+                            }
+                            bot[cc] = c[R - 1];
+                        }
+                    }
+                }
+                __syncwarp();          // (the region above is divergent) every lane has read its top values: publish the new ones
+#pragma unroll
+                for (int p = 0; p < NP; ++p) write_part(p, bot[2 * p], bot[2 * p + 1]);
+                __syncwarp();
+            }
+            // direction words of the tile: one vector store per lane, 32*NWT contiguous words per warp
+            {
+                uint32_t acc[NWT];
+#pragma unroll
+                for (int w = 0; w < NWT; ++w) {
+                    uint32_t a = accp[0][w];
+#pragma unroll
+                    for (int cc = 1; cc < C; ++cc) if ((2 * (cc * R) >> 5) <= w && (2 * (cc * R + R - 1) >> 5) >= w) a += accp[cc][w];
+                    acc[w] = a;
+                }
+                if (NWT == 1) dirW[0] = acc[0];
+                else if (NWT == 2) *reinterpret_cast<uint2 *>(dirW) = make_uint2(acc[0], acc[1 % NWT]);
+                else *reinterpret_cast<uint4 *>(dirW) = make_uint4(acc[0], acc[1 % NWT], acc[2 % NWT], acc[3 % NWT]);
+                dirW += 32 * NWT;
+            }
+            // bottom row of the strip -> ring (lane 31): two {4H, tag} words per 128-bit store
+            if (MODE != 0) {
+                const uint32_t wr = MODE == 1 ? writesFlag : MODE == 2 ? (kb >= 0 ? writesFlag : 0u) : (kb < nTiles ? writesFlag : 0u);
+                st_row_words_if<C>(wr, rowW, bot, (uint32_t)(myTagHi >> 32));
+            } else if (active && writesRow) {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc)
+                    if (cc < ncols) st_volatile_u64(rowW + cc, myTagHi | (uint32_t)bot[cc]);
+            }
+            rowW += C;
+            if (LINKED && MODE == 1 && A.dbg && kb == 8008 && lane == 31) dbgWrite = gtime();
+            if (LOCAL) {
+                const bool cand = active && rowsValid && tmax > 0 && tmax >= bestv && tmax >= gmCached;
+                if (__any_sync(0xffffffffu, cand)) {
+                    if (cand) {
+                        const int key = tile_locate<R, C>(tmax, KL, KT, cornerIn, cin, topIn, pw, ncols);
+                        const int ci = row0 + lane * R + key / C + 1, cj = kb * C + key % C + 1 + (int)A.col0;
+                        if (key < R * C && (tmax > bestv || ci < besti)) { bestv = tmax; besti = ci; bestj = cj; }
+                        if (tmax > gmCached) { atomicMax(A.gmax, tmax); gmCached = tmax; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) pw[cc][q] = pwN[cc][q];
+        };
+
+        // groups of TG macro-steps: ramp-up (first 32), steady state, then the generic tail (last partial tile + drain)
+        // (the last tile of a lane -- full or partial -- always belongs to the drain, which parks the final column)
+        const int nStraight = nTiles - 1;
+        const int kRamp = nStraight >= 32 ? 32 : 0;
+        if (LINKED && A.dbg && lane == 0) A.dbg[3 * A.n_strips + 4 * s] = gtime();
+        for (int k = 0; k < kEnd; k += TG) {
+            top_upkeep(k + 1);
+            if (k >= 32 && (k & 31) == 0) text_upkeep(k);
+            if (LINKED && A.dbg && lane == 0) {
+                if (k == 32) A.dbg[3 * A.n_strips + 4 * s + 1] = gtime();
+                if (k + TG > nStraight && k < nStraight + TG) A.dbg[3 * A.n_strips + 4 * s + 2] = gtime();
+                if (k + TG >= kEnd) A.dbg[3 * A.n_strips + 4 * s + 3] = gtime();
+            }
+            if (k + TG <= kRamp) {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) {
+                    macro_step(k + u, std::integral_constant<int, 2>{});
+                    if (u == TG_REQ && hasUp) request_top(k + 1 + TG);
+                }
+            } else if (k >= kRamp && kRamp > 0 && k + TG <= nStraight) {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) {
+                    macro_step(k + u, std::integral_constant<int, 1>{});
+                    if (u == TG_REQ && hasUp) request_top(k + 1 + TG);
+                }
+            } else if (kRamp > 0) {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) {
+                    if (k + u < kEnd) macro_step(k + u, std::integral_constant<int, 3>{});
+                    if (u == TG_REQ && hasUp) request_top(k + 1 + TG);
+                }
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < TG; ++u) {
+                    if (k + u < kEnd) macro_step(k + u, std::integral_constant<int, 0>{});
+                    if (u == TG_REQ && hasUp) request_top(k + 1 + TG);
+                }
+            }
+        }
+        if (kRamp == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) cfin[r] = c[r];
+        }
+
+        // ---- strip results ----
+        if (LINKED && A.dbg && lane == 0) {
+            A.dbg[3 * s + 2] = gtime();
+            unsigned long long *x = A.dbg + 7 * (size_t)A.n_strips + 4 * (size_t)s;
+            x[0] = dbgSpins; x[1] = dbgSpinNs; x[2] = dbgStalls; x[3] = dbgRampStalls;
+            unsigned long long *y = A.dbg + 11 * (size_t)A.n_strips + 2 * (size_t)s;
+            y[0] = dbgEnter; y[1] = dbgExit;
+        }
+        if (LINKED && A.dbg && lane == 31) A.dbg[13 * (size_t)A.n_strips + s] = dbgWrite;
+        if (LINKED && A.right_col64) {          // linked slices: straight into the right neighbour's memory
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int gi = row0 + lane * R + r + 1;
+                if (gi <= m) st_volatile_u64(A.right_col64 + gi, ((unsigned long long)A.xtag << 32) | (unsigned long long)(uint32_t)cfin[r]);
+            }
+        }
+        if (A.right_col) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int gi = row0 + lane * R + r + 1;
+                if (gi <= m) A.right_col[gi] = cfin[r];
+            }
+            if (s == 0 && lane == 0 && A.row_base == 0) A.right_col[0] = LOCAL ? 0 : -SCALE * A.gap * (int)(A.col0 + A.n);
+        }
+        if (LOCAL) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+                const bool take = ov > bestv || (ov == bestv && (oi < besti || (oi == besti && oj < bestj)));
+                if (take) { bestv = ov; besti = oi; bestj = oj; }
+            }
+            if (lane == 0) { A.cand_v[s] = bestv; A.cand_i[s] = bestv > 0 ? besti : 0; A.cand_j[s] = bestv > 0 ? bestj : 0; }
+        } else {
+            const int lm = (m - 1 - row0) / R;
+            if (m - 1 >= row0 && m - 1 < row0 + ROWS && lane == lm) {
+                const int rm = (m - 1 - row0) % R;
+                int v = cfin[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) v = (r == rm) ? cfin[r] : v;
+                *A.score = v / SCALE;
+            }
+        }
+    }
+}
+
+} // namespace sa

@@ -29,6 +29,9 @@ struct TbLayout {
     const uint32_t *dirs;  uint64_t strip_stride;
     int R, CB, NW, ROWS, cbShift;
     int n, m;
+    // tile layout of tile_fill_kernel (sa_tile.cuh): C > 0 columns per tile, NW = R*C/16 words per lane and macro-step;
+    // C == 0 selects the warp-step-major layout of long_fill_kernel
+    int C, cShift;
 };
 
 struct TbState {            // device-resident scalars of one traceback
@@ -81,10 +84,18 @@ __device__ __forceinline__ int tb_fetch(const TbLayout &L, TbCursor &cur, const 
     // one division by R; ROWS = 32*R and CB is a power of two
     const int gl = (i - 1) / L.R, r = (i - 1) - gl * L.R;
     const int s = gl >> 5, ll = gl & 31;
-    const int k = (j - 1) + ll;
-    const int kb = k >> L.cbShift, kk = k & (L.CB - 1);
-    const int bit = (kk * L.R + r) * 2;
-    const size_t addr = (size_t)s * L.strip_stride + (size_t)(kb * L.NW + (bit >> 5)) * 32 + ll;
+    int bit;
+    size_t addr;
+    if (L.C) {
+        const int k = ((j - 1) >> L.cShift) + ll, cc = (j - 1) & (L.C - 1);
+        bit = (cc * L.R + r) * 2;
+        addr = (size_t)s * L.strip_stride + ((size_t)k * 32 + ll) * L.NW + (bit >> 5);
+    } else {
+        const int k = (j - 1) + ll;
+        const int kb = k >> L.cbShift, kk = k & (L.CB - 1);
+        bit = (kk * L.R + r) * 2;
+        addr = (size_t)s * L.strip_stride + (size_t)(kb * L.NW + (bit >> 5)) * 32 + ll;
+    }
     if (addr != cur.cachedAddr) { cur.cachedAddr = addr; cur.cachedWord = __ldg(L.dirs + addr); }
     return (cur.cachedWord >> (bit & 31)) & 3;
 }

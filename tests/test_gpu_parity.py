@@ -655,3 +655,99 @@ def test_device_batch_marks_pairs_it_cannot_take(sa, aligner, oracle):
         assert int(out["results"]["score"][i]) == -2**31 and int(out["results"]["aln_len"][i]) == 0
     keep = np.flatnonzero(lens_n <= cut_n).astype(np.uint64)
     assert oracle.check_batch(1, 23, mat, 5, T, toff, P, poff, out, idx=keep) == (0, -1)
+
+
+TILE_SHAPES = ["4,4", "8,4", "8,2", "4,8", "2,8", "16,4", "8,8"]
+
+
+@pytest.mark.parametrize("tile", TILE_SHAPES)
+def test_goldens_through_tile_kernel(aligner, force_path, monkeypatch, tile):
+    """Short and medium goldens forced through the register-tiled long-pair kernel (sa_tile.cuh) at every tile shape."""
+    force_path("long")
+    monkeypatch.setenv("SA_TILE", tile)
+    gs = [g for g in helpers.goldens() if helpers.has_inputs(g) and g["n"] * g["m"] < 3e6]
+    k = TILE_SHAPES.index(tile)
+    for g in gs[k % 2::2]:
+        t, p, mat = helpers.golden_inputs(g)
+        a = aligner.align(g["mode"], g["alpha"], mat, g["gap"], t, p)
+        helpers.check_against_golden(a, g)
+
+
+@pytest.mark.parametrize("tile", TILE_SHAPES)
+def test_tile_kernel_random_and_ties_vs_oracle(aligner, oracle, force_path, monkeypatch, tile):
+    """Random pairs of every length class around the tile / group boundaries (n mod C, n around 32*C and TG*C, m around
+    32*R), random matrices and gaps, both modes; then low-complexity inputs where every cell is a tie and the SW arg-max
+    has many equal candidates in different tiles, lanes and strips."""
+    force_path("long")
+    monkeypatch.setenv("SA_TILE", tile)
+    R, C = (int(x) for x in tile.split(","))
+    rng = np.random.default_rng(hash(tile) % 10000)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+    lens = [1, 2, C - 1, C, C + 1, 31 * C, 32 * C, 32 * C + 1, 33 * C + C // 2, 8 * C * 5 + 3, 700, 1500]
+    rows = [1, R, R + 1, 32 * R - 1, 32 * R, 32 * R + 1, 70 * R, 1300]
+    for it in range(60):
+        alpha = 4 if it % 2 == 0 else 23
+        mat = rng.integers(-9, 12, (alpha, alpha)).astype(np.int32) if it % 3 == 0 else (blast if alpha == 4 else b62)
+        n, m = lens[it % len(lens)], rows[(it // 2) % len(rows)]
+        t = rng.integers(0, alpha, max(1, n), dtype=np.uint8)
+        if it % 4 < 2 and m <= len(t):
+            p = t[:m].copy()
+            p[rng.random(len(p)) < 0.1] = rng.integers(0, alpha)
+        else:
+            p = rng.integers(0, alpha, m, dtype=np.uint8)
+        gap = int(rng.integers(0, 12))
+        for mode in (0, 1):
+            assert_same(aligner.align(mode, alpha, mat, gap, t, p), oracle.align(mode, alpha, mat, gap, t, p),
+                        (tile, it, alpha, mode, gap, len(t), len(p)))
+    for mode in (0, 1):
+        for t, p in ((np.zeros(333, np.uint8), np.zeros(297, np.uint8)),
+                     (np.tile(np.arange(4, dtype=np.uint8), 190), np.tile(np.arange(4, dtype=np.uint8), 133)),
+                     (np.tile(np.array([0, 0, 1], np.uint8), 300), np.tile(np.array([0, 1], np.uint8), 260))):
+            for gap in (0, 1, 5):
+                assert_same(aligner.align(mode, 4, blast, gap, t, p), oracle.align(mode, 4, blast, gap, t, p), (tile, mode, gap, len(t)))
+
+
+@pytest.mark.parametrize("tile", ["4,4", "8,4", "8,2"])
+def test_tile_kernel_slices_and_row_chunks(sa, oracle, monkeypatch, tile):
+    """Column slices (int32 border columns, row chunks, linked {4H, tag} borders) through the tiled kernel."""
+    from sa_b200 import strips
+    import synth
+    monkeypatch.setenv("SA_TILE", tile)
+    rng = np.random.default_rng(77)
+    blast = helpers.matrices()["dna/blast.txt"]
+    t = rng.integers(0, 4, 2700, dtype=np.uint8)
+    p = synth.mutate_indices_numpy(t, rng, 4)[:2450]
+    want = oracle.align(0, 4, blast, 5, t, p)
+    for world in (2, 3):
+        assert_same(_strip_align(sa, 4, blast, 5, t, p, world), want, (tile, world))
+        assert_same(_strip_align(sa, 4, blast, 5, t, p, world, chunks=3), want, (tile, world, "row chunks"))
+        als = [sa.Aligner(0) for _ in range(world)]
+        try:
+            eng = [strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, len(t), p)
+                   for al, (c0, w) in zip(als, strips.slice_columns(len(t), world))]
+            for tag in (1, 2):
+                score, at, ap, ti, pi = strips.align_pair_strips_linked_local(eng, len(p), tag=tag)
+                assert_same(sa.Alignment(score, len(at), ti, pi, at, ap), want, (tile, world, "linked", tag))
+            for e in eng:
+                if hasattr(e, "border_ptr"):
+                    e.al.peer_free(e.border_ptr)
+        finally:
+            for al in als:
+                al.close()
+
+
+def test_tile_kernel_many_strips_in_waves(aligner, oracle, force_path, monkeypatch):
+    """More strips than resident warps: the persistent loop takes strips in waves and the boundary ring wraps."""
+    force_path("long")
+    monkeypatch.setenv("SA_TILE", "2,8")
+    import synth
+    rng = np.random.default_rng(3)
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+    t = rng.integers(0, 23, 600, dtype=np.uint8)
+    p = np.concatenate([synth.mutate_indices_numpy(t, rng, 23) for _ in range(520)])[:300000]       # 4688 strips of 64 rows
+    for mode in (0, 1):
+        got = aligner.align(mode, 23, b62, 5, t, p)
+        s, _ = oracle.score_only(mode, 23, b62, 5, t, p)
+        assert got.score == s
+        assert oracle.rescore(got.aligned_text, got.aligned_pattern, 23, b62, 5) == got.score

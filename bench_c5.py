@@ -34,35 +34,23 @@ def rescore(at, ap, S, gap):
     return int(S[b[both], a[both]].sum() - gap * int((~both).sum()))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--length", type=int, default=1_000_000)
-    ap.add_argument("--steps", type=int, default=1)
-    ap.add_argument("--chunks", type=int, default=1,
-                    help="row chunks per slice; 1 = slices run one after the other.  (Measured: chunks do not pay with the "
-                         "present kernel -- every launch still sweeps the whole slice width serially -- see DESIGN.md 6.)")
-    ap.add_argument("--no-linked", dest="linked", action="store_false",
-                    help="default (N >= 2): the border column is handed over INSIDE the launches (peer memory through CUDA "
-                         "IPC; every rank launches its slice at once and the strips of neighbouring GPUs overlap).  With "
-                         "--no-linked the slices run one after the other with NCCL send/recv of the whole column")
-    ap.set_defaults(linked=True)
-    ap.add_argument("--check", action="store_true", help="also run the single-matrix path on rank 0 and compare (needs the memory)")
-    args = ap.parse_args()
+def golden_for(length):
+    """The CPU oracle's score for this length (tests/golden/c5_golden.json, made by tests/golden/make_c5_golden.py)."""
+    f = os.path.join(ROOT, "tests", "golden", "c5_golden.json")
+    if not os.path.exists(f):
+        return None
+    return json.load(open(f)).get(str(length))
+
+
+def run_c5(sa, rank, world, local_rank, length, steps=1, linked=True, chunks=1, check=False):
+    """One global alignment of `length` x ~0.95 length over `world` GPUs (column slices); torch.distributed must be
+    initialised when world > 1.  Returns the result dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
-    from __graft_entry__ import load_package
     import synth
-    sa = load_package()
     from sa_b200 import strips
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench_c5.py: no CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    t, p = synth.synthetic_pair(args.length, 777, 778)
+    t, p = synth.synthetic_pair(length, 777, 778)
     n, m = len(t), len(p)
     blast = np.array([[5 if i == j else -4 for j in range(4)] for i in range(4)], np.int32)   # scoreMatrices/dna/blast.txt
     c0, w = strips.slice_columns(n, world)[rank]
@@ -80,15 +68,15 @@ def main():
         torch.cuda.synchronize()
 
     best = None
-    for _ in range(args.steps):
+    for _ in range(steps):
         barrier()
         t0 = time.perf_counter()
-        if world > 1 and args.linked:
+        if world > 1 and linked:
             res = strips.align_pair_strips_linked(eng, m, rank, world)
         elif world > 1:
-            res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer, chunks=args.chunks)
+            res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer, chunks=chunks)
         else:
-            res = strips.align_pair_strips_local([eng], m, chunks=args.chunks)
+            res = strips.align_pair_strips_local([eng], m, chunks=chunks)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt, eng.fill_ms or 0.0], dtype=torch.float64, device=dev)
@@ -102,32 +90,68 @@ def main():
         if best is None or wall < best[0]:
             best = (wall, fills, res)
     wall, fills, (score, at, apat, ti, pi) = best
+    out = None
     if rank == 0:
         letters = np.frombuffer(b"ATCG", np.uint8)
+        gold = golden_for(length)
         checks = dict(rescore_equals_score=rescore(at, apat, blast.astype(np.int64), 5) == score,
                       text_spelled=at.replace(b"-", b"") == letters[t].tobytes(),
                       pattern_spelled=apat.replace(b"-", b"") == letters[p].tobytes(),
-                      starts=[ti, pi])
-        if args.check:
+                      starts=[ti, pi],
+                      score_equals_cpu_oracle=(score == gold["score"] and (n, m) == (gold["n"], gold["m"])) if gold else None)
+        if check:
             one = sa.Aligner(local_rank)
             a = one.align(0, 4, blast, 5, t, p)
             checks["equals_single_matrix_path"] = (a.score, a.aligned_text, a.aligned_pattern) == (score, at, apat)
             one.close()
         cells = (n + 1) * (m + 1)
-        print(json.dumps(dict(metric="GCUPS incl. traceback (config 5, column slices)", value=cells / wall / 1e9, unit="GCUPS",
-                              n_gpus=world, steps=args.steps, seconds=wall, fill_ms_per_rank=fills,
-                              fill_gcups_per_rank=[(w_ * (m + 1)) / (f * 1e6) if f else None
-                                                   for (_, w_), f in zip(strips.slice_columns(n, world), fills)],
-                              score=score, aln_len=len(at), checks=checks, dtype="int32", data="synthetic",
-                              config=dict(workload=f"c5: NW {n} x {m} DNA, blast, gap 5", slices=world,
-                                          row_chunks=args.chunks,
-                                          pipeline="linked in-launch hand-off over peer memory (strips of neighbouring GPUs overlap)" if args.linked and world > 1
-                                          else "rank k fills row chunk c while rank k+1 fills chunk c-1" if args.chunks > 1
-                                          else "slices run one after the other"))))
+        out = dict(metric="GCUPS incl. traceback (config 5, column slices)", value=cells / wall / 1e9, unit="GCUPS",
+                   n_gpus=world, steps=steps, seconds=wall, fill_ms_per_rank=fills,
+                   fill_gcups_per_rank=[(w_ * (m + 1)) / (f * 1e6) if f else None
+                                        for (_, w_), f in zip(strips.slice_columns(n, world), fills)],
+                   score=score, aln_len=len(at), checks=checks, dtype="int32", data="synthetic",
+                   config=dict(workload=f"c5: NW {n} x {m} DNA, blast, gap 5", slices=world, row_chunks=chunks,
+                               pipeline="linked in-launch hand-off over peer memory (strips of neighbouring GPUs overlap)" if linked and world > 1
+                               else "rank k fills row chunk c while rank k+1 fills chunk c-1" if chunks > 1
+                               else "slices run one after the other"))
+    eng.linked_release(barrier if world > 1 else None)
+    del eng
+    al.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--length", type=int, default=1_000_000)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="row chunks per slice; 1 = slices run one after the other.  (Measured: chunks do not pay with the "
+                         "present kernel -- every launch still sweeps the whole slice width serially -- see DESIGN.md 6.)")
+    ap.add_argument("--no-linked", dest="linked", action="store_false",
+                    help="default (N >= 2): the border column is handed over INSIDE the launches (peer memory through CUDA "
+                         "IPC; every rank launches its slice at once and the strips of neighbouring GPUs overlap).  With "
+                         "--no-linked the slices run one after the other with NCCL send/recv of the whole column")
+    ap.set_defaults(linked=True)
+    ap.add_argument("--check", action="store_true", help="also run the single-matrix path on rank 0 and compare (needs the memory)")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    sa = load_package()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_c5.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run_c5(sa, rank, world, local_rank, args.length, args.steps, args.linked, args.chunks, args.check)
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    al.close()
 
 
 if __name__ == "__main__":

@@ -370,6 +370,42 @@ def unpack_batch(out, i) -> Alignment:
                      out["aligned_text"][off:off + ln].tobytes(), out["aligned_pattern"][off:off + ln].tobytes())
 
 
+class _Options(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("devices", C.c_int32 * 8)]
+
+
+def align_batch_multi(devices, mode, alpha, matrix, gap, text, text_off, pattern, pattern_off, out=None, alphabet=None):
+    """sa_align_batch_multi: one host batch sharded over ``devices`` (CUDA ordinals) inside this process, one host thread
+    and one cached context per device, no collective."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    pattern = np.ascontiguousarray(pattern, dtype=np.uint8)
+    text_off = np.ascontiguousarray(text_off, dtype=np.int64)
+    pattern_off = np.ascontiguousarray(pattern_off, dtype=np.int64)
+    N = len(text_off) - 1
+    arena = int(text_off[N] - text_off[0] + pattern_off[N] - pattern_off[0])
+    if out is None:
+        out = dict(results=np.zeros(N, RESULT_DTYPE), aln_off=np.zeros(N, np.uint64),
+                   aligned_text=np.empty(max(arena, 1), np.uint8), aligned_pattern=np.empty(max(arena, 1), np.uint8))
+    m = np.ascontiguousarray(np.asarray(matrix, np.int32).ravel())
+    sc = _Scoring(int(mode), int(alpha), m.ctypes.data, int(gap), alphabet or _alphabet_for(alpha))
+    opt = _Options(len(devices), (C.c_int32 * 8)(*list(devices)))
+    b = _Batch(N, text.ctypes.data, text_off.ctypes.data, pattern.ctypes.data, pattern_off.ctypes.data)
+    o = _BatchOut(out["results"].ctypes.data, out["aln_off"].ctypes.data, out["aligned_text"].ctypes.data,
+                  out["aligned_pattern"].ctypes.data, arena)
+    L = lib()
+    rc = L.sa_align_batch_multi(C.byref(opt), C.byref(sc), C.byref(b), C.byref(o))
+    if rc != 0:
+        raise SaError(rc, L.sa_status_string(rc).decode())
+    return out
+
+
+def multi_timing(k: int) -> dict:
+    """Timing of device k of the last align_batch_multi call."""
+    t = _Timing()
+    lib().sa_multi_last_timing(int(k), C.byref(t))
+    return {f: getattr(t, f) for f, _ in _Timing._fields_}
+
+
 def partition_batch(text_off, pattern_off, world: int) -> np.ndarray:
     """Cell-balanced contiguous split of a batch over ``world`` ranks (sa_partition_batch)."""
     text_off = np.ascontiguousarray(text_off, dtype=np.int64)

@@ -772,7 +772,7 @@ struct LongPlan {
 // latencies and the one-column kernel with tall strips issues fewer instructions per cell: 59 ms against 75 ms.
 // SA_TILE="R,C" forces a tile shape; SA_LONG_R or SA_LONG_KERNEL=strip force the one-column kernel (always the path
 // of wide score matrices).
-bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int *R, int *C)
+bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int slices, int *R, int *C)
 {
     (void)n;
     if (std::getenv("SA_LONG_R")) return false;
@@ -781,9 +781,11 @@ bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int *R, int *
     // passes of the parallel traceback short (3 903 x 3 698: fill + traceback 0.82 ms against 0.99).  Local alignments stay
     // on the one-column kernel: the per-tile arg-max test costs the tiled sweep its advantage (100 k x 95 k SW: 29.6 ms
     // tiled, 27.8 ms one-column; both ~2.8x the global fill -- the next thing to fix on this path).
+    // A column slice of a pair that is spread over 4 or more GPUs is latency-bound again, whatever its height: GPU k
+    // starts when strip 0 has crossed k slices, and a tiled strip crosses a 125 000-column slice in 8 ms against 17 ms.
     int r = 8, c = 2;
     if (traceback && m <= 16000) { r = 4; c = 4; }
-    bool use = m <= 300000 && !local;
+    bool use = (m <= 300000 || slices >= 4) && !local;
     if (const char *e = std::getenv("SA_TILE")) {
         int er = 0, ec = 0;
         if (std::sscanf(e, "%d,%d", &er, &ec) == 2 && tile_cfg_exists(er, ec)) { r = er; c = ec; use = true; }
@@ -806,7 +808,7 @@ bool fits_s32(const sa_scoring *sc, uint64_t n, uint64_t m)
     return (long double)big * (long double)(n + m + 2) * SCALE < 2147483000.0L;
 }
 
-int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P, bool traceback = true, bool linked = false)
+int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, LongPlan *P, bool traceback = true, bool linked = false, int slices = 1)
 {
     const bool local = sc->mode == SA_LOCAL;
     if (!fits_s32(sc, n, m)) return SA_ERR_SCORE_RANGE;
@@ -827,7 +829,7 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
     if (wide) R = WIDE_R;
     int tR = 0, tC = 0;
     P->C = 0;
-    if (!wide && pick_tile(n, m, traceback, local, &tR, &tC)) {
+    if (!wide && pick_tile(n, m, traceback, local, slices, &tR, &tC)) {
         P->R = tR; P->C = tC; P->CB = 1; P->NW = tile_nwt(tR, tC);
         P->n_strips = (uint32_t)((m + 32ull * tR - 1) / (32ull * tR));
         P->smem = tile_smem_bytes(tR, tC, sc->alphabet_size);
@@ -1335,7 +1337,7 @@ int sa_strip_begin(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text,
     // the strip height follows the rows that are in flight together: one chunk
     const uint64_t hint = chunk_rows_hint == 0 || chunk_rows_hint > m ? m : chunk_rows_hint;
     LongPlan P;
-    rc = plan_long(ctx, sc, n, hint, &P);
+    rc = plan_long(ctx, sc, n, hint, &P, true, false, (int)std::min<uint64_t>(64, (text_total + n / 2) / n));
     if (rc) return rc;
     const uint64_t ROWS = 32ull * P.R;
     const uint64_t chunk = hint >= m ? m : (hint + ROWS - 1) / ROWS * ROWS;

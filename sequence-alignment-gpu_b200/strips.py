@@ -101,6 +101,7 @@ class GpuStripEngine:
         """right_handle: IPC handle of the right neighbour's border buffer (another process); right_ptr: its device
         pointer when the neighbour lives in this process (tests on one GPU)."""
         self.right_ptr = self.al.peer_open(right_handle) if right_handle is not None else (right_ptr or 0)
+        self._right_mapped = right_handle is not None
 
     def fill_linked(self, tag):
         torch = self.torch
@@ -115,6 +116,19 @@ class GpuStripEngine:
     def linked_finish(self):
         self.al.strip_linked_status(stream=self.stream.cuda_stream)       # synchronises; raises if a neighbour never delivered
         self.fill_ms = self._e0.elapsed_time(self._e1)
+
+    def linked_release(self, barrier=None):
+        """Unmaps the right neighbour's border buffer, then (after `barrier()`, so that nobody still has it mapped)
+        frees this slice's own."""
+        if getattr(self, "_right_mapped", False):
+            self.al.peer_close(self.right_ptr)
+            self._right_mapped = False
+        self.right_ptr = 0
+        if barrier is not None:
+            barrier()
+        if hasattr(self, "border_ptr"):
+            self.al.peer_free(self.border_ptr)
+            del self.border_ptr
 
     def score(self):
         return int(self.d_score.item())

@@ -6,6 +6,8 @@
 //   dropin_main --batch <case file>            alignSequenceGPUBatch on the requests of a binary case file, one line
 //                                              per pair on stdout:  score len startText startPattern text pattern
 //   dropin_main --twice <reference CLI args>   the same Response object through alignSequenceGPU twice (buffer reuse)
+//   dropin_main --return <reference CLI args>  prints what alignSequenceGPU returns: 0, or with the -DBENCHMARK build of
+//                                              the library the microseconds of fill + D2H (tests/benchmarks.cu:171-175)
 #include "SequenceAlignment.hpp"
 
 #include <cstdio>
@@ -79,5 +81,13 @@ int main(int argc, const char *argv[])
 {
     if (argc >= 3 && !std::strcmp(argv[1], "--batch")) return run_batch(argv[2]);
     if (argc >= 2 && !std::strcmp(argv[1], "--twice")) return run_cli(argc - 1, argv + 1, 2);
+    if (argc >= 2 && !std::strcmp(argv[1], "--return")) {
+        SA::Request request;
+        SA::Response response;
+        if (parseArguments(argc - 1, argv + 1, &request)) return 1;
+        const uint64_t r = SA::alignSequenceGPU(request, &response);
+        std::printf("%llu %d\n", (unsigned long long)r, response.score);
+        return 0;
+    }
     return run_cli(argc, argv, 1);
 }

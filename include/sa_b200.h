@@ -209,6 +209,12 @@ int sa_read_fasta_batch(const char *path, const char *alphabet, int alphabet_siz
                         int64_t **offsets, uint64_t *n_records, char *bad_letter);
 void sa_free(void *p);
 
+/* Identity / gap counts of the alignment the last sa_align call on this context produced, counted
+ * on the device during string emission (prettyAlignmentPrint's "# Identity" and "# Gaps", utilities.cpp:262-283):
+ * identity = columns with the same letter in both strings, gaps = columns with a gap character in either. */
+typedef struct { uint64_t identity; uint64_t gaps; } sa_stats;
+int sa_last_stats(sa_context *ctx, sa_stats *out);
+
 /* The report of prettyAlignmentPrint (utilities.cpp:253-315), byte for byte: returns the size of the full report and
  * writes at most cap bytes of it into out; *identity / *gaps (may be NULL) receive the two counts. */
 uint64_t sa_pretty_print(const char *aligned_text, const char *aligned_pattern, uint64_t len, uint64_t start_text,
@@ -238,6 +244,9 @@ typedef struct {
     char      *aligned_text;     /* arena */
     char      *aligned_pattern;  /* arena */
     uint64_t   arena_capacity;   /* bytes available in each arena */
+    uint32_t  *stats;            /* optional (NULL = not wanted): 2 per pair, {identity, gaps} -- the counts of
+                                  * prettyAlignmentPrint (utilities.cpp:262-283), taken on the device while the
+                                  * strings are emitted */
 } sa_batch_out;
 
 /* HOST buffers; copies in, aligns on the device, copies results out, pipelined

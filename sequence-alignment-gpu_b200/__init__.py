@@ -81,7 +81,11 @@ class _Batch(C.Structure):
 
 class _BatchOut(C.Structure):
     _fields_ = [("results", C.c_void_p), ("aln_off", C.c_void_p), ("aligned_text", C.c_void_p),
-                ("aligned_pattern", C.c_void_p), ("arena_capacity", C.c_uint64)]
+                ("aligned_pattern", C.c_void_p), ("arena_capacity", C.c_uint64), ("stats", C.c_void_p)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("identity", C.c_uint64), ("gaps", C.c_uint64)]
 
 
 RESULT_DTYPE = np.dtype([("score", np.int32), ("_pad", np.int32), ("aln_len", np.uint64),
@@ -316,17 +320,23 @@ class Aligner:
         sc = self._scoring(mode, alpha, matrix, gap, alphabet)
         b = _Batch(N, text.ctypes.data, text_off.ctypes.data, pattern.ctypes.data, pattern_off.ctypes.data)
         o = _BatchOut(out["results"].ctypes.data, out["aln_off"].ctypes.data, out["aligned_text"].ctypes.data,
-                      out["aligned_pattern"].ctypes.data, arena)
+                      out["aligned_pattern"].ctypes.data, arena, out["stats"].ctypes.data if out.get("stats") is not None else None)
         self._check(self._L.sa_align_batch(self._ctx, C.byref(sc), C.byref(b), C.byref(o)))
         return out
+
+    def last_stats(self):
+        """(identity, gaps) of the last align() call, counted on the device during string emission (sa_last_stats)."""
+        st = _Stats()
+        self._check(self._L.sa_last_stats(self._ctx, C.byref(st)))
+        return int(st.identity), int(st.gaps)
 
     # -- device-resident batch (sa_align_batch_device): raw device pointers, e.g. torch data_ptr()
     def align_batch_device(self, mode, alpha, matrix, gap, n_pairs, d_text, d_text_off, d_pattern, d_pattern_off,
                            d_results, d_aln_off, d_out_text, d_out_pattern, arena_capacity, max_text_len,
-                           max_pattern_len, stream=0, alphabet=None):
+                           max_pattern_len, stream=0, alphabet=None, d_stats=0):
         sc = self._scoring(mode, alpha, matrix, gap, alphabet)
         b = _Batch(n_pairs, d_text, d_text_off, d_pattern, d_pattern_off)
-        o = _BatchOut(d_results, d_aln_off, d_out_text, d_out_pattern, arena_capacity)
+        o = _BatchOut(d_results, d_aln_off, d_out_text, d_out_pattern, arena_capacity, d_stats or None)
         self._check(self._L.sa_align_batch_device(self._ctx, C.byref(sc), C.byref(b), C.byref(o),
                                                   int(max_text_len), int(max_pattern_len), C.c_void_p(stream)))
 
@@ -391,7 +401,7 @@ def align_batch_multi(devices, mode, alpha, matrix, gap, text, text_off, pattern
     opt = _Options(len(devices), (C.c_int32 * 8)(*list(devices)))
     b = _Batch(N, text.ctypes.data, text_off.ctypes.data, pattern.ctypes.data, pattern_off.ctypes.data)
     o = _BatchOut(out["results"].ctypes.data, out["aln_off"].ctypes.data, out["aligned_text"].ctypes.data,
-                  out["aligned_pattern"].ctypes.data, arena)
+                  out["aligned_pattern"].ctypes.data, arena, out["stats"].ctypes.data if out.get("stats") is not None else None)
     L = lib()
     rc = L.sa_align_batch_multi(C.byref(opt), C.byref(sc), C.byref(b), C.byref(o))
     if rc != 0:

@@ -68,6 +68,7 @@ struct Slot {              // per-chunk device buffers of the host batch path
     cudaStream_t stream = nullptr;
     DevBuf text, pattern, toff, poff, results, alnoff, outT, outP, dirs, fill, order, snap;
     DevBuf packT, packP, noff;             // staged host path: packed strings of the chunk
+    DevBuf stats;                          // optional per-pair {identity, gaps}
     cudaEvent_t packed = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t in = nullptr, out = nullptr;      // staged host path: inputs landed / outputs drained
@@ -118,6 +119,9 @@ struct sa_context {
         char alphabet[40] = {};
     } strip;
     sa_timing timing = {};
+    const void *stats_src = nullptr;        // device: {identity, gaps} u64 of the last long-pair traceback
+    sa_stats last_stats = {};               // identity / gaps of the last single-pair alignment
+    bool have_stats = false;
     // per-kernel timing: (before fill, after fill, after traceback) event triples of the last call
     std::vector<cudaEvent_t> evpool;
     size_t evused = 0;
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactArgs A)
 // BATCH_MAX_ROWS or whose text exceeds BATCH_MAX_TEXT are left untouched (the host path aligns
 // them one by one through the long-pair kernels).
 int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_result *d_results,
-                  uint64_t *d_alnoff, char *d_outT, char *d_outP, uint32_t max_n, uint32_t max_m,
+                  uint64_t *d_alnoff, uint32_t *d_stats, char *d_outT, char *d_outP, uint32_t max_n, uint32_t max_m,
                   uint32_t *d_dirs, size_t dirs_words, void *d_fill, void *d_sort, DevBuf *snapbuf, cudaStream_t st,
                   uint32_t first, uint32_t count, cudaStream_t stTrace = nullptr, cudaEvent_t evFillDone = nullptr,
                   bool tbShare = false)
@@ -670,7 +674,7 @@ int enqueue_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_r
     R.score = d_score; R.end_i = d_ei; R.end_j = d_ej;
     R.S = ctx->dS.as<int32_t>(); R.alpha = sc->alphabet_size; R.gap = sc->gap; R.local = local;
     std::memcpy(R.alphabet, sc->alphabet, sc->alphabet_size + 1);
-    R.results = d_results; R.aln_off = d_alnoff; R.out_text = d_outT; R.out_pattern = d_outP;
+    R.results = d_results; R.aln_off = d_alnoff; R.out_text = d_outT; R.out_pattern = d_outP; R.stats = d_stats;
     // tbShare: another chunk's fill follows on the other stream -- one block per SM leaves it its three blocks per SM
     // (the carve-out preference follows: maximum shared memory while sharing SMs with fill blocks, the default --
     // more L1 for the scattered tag reads -- when the traceback has the GPU to itself)
@@ -909,6 +913,7 @@ int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, u
         SA_TRY(ctx->tbbuf.reserve(off), SA_ERR_MEMORY);
         char *base = ctx->tbbuf.as<char>();
         T.st = reinterpret_cast<TbState *>(base + oSt); T.X = reinterpret_cast<int *>(base + oX);
+        ctx->stats_src = &T.st->identity;
         T.seg_len = reinterpret_cast<unsigned long long *>(base + oLen);
         T.seg_delta = reinterpret_cast<long long *>(base + oDel); T.seg_min = reinterpret_cast<long long *>(base + oMin);
         T.seg_off = reinterpret_cast<unsigned long long *>(base + oOff); T.fa = reinterpret_cast<uint32_t *>(base + oFa);
@@ -990,6 +995,8 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
         std::memcpy(T.alphabet, sc->alphabet, sc->alphabet_size + 1);
         T.cap = cap; T.out_text = d_outT; T.out_pattern = d_outP; T.res = d_res;
         T.emit = traceback ? 1 : 0;
+        T.stats = reinterpret_cast<unsigned long long *>(ctx->misc.as<char>() + 40);      // (bytes 40..55 are free: score at 32, gmax at 48 is zeroed before the fill and not used afterwards)
+        ctx->stats_src = T.stats;
         long_traceback_kernel<<<1, 32, 0, st>>>(T);
         SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;
@@ -1128,7 +1135,7 @@ void sa_destroy(sa_context *ctx)
         b->release();
     ctx->pin.release();
     for (auto &s : ctx->slot) {
-        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order, &s.snap, &s.packT, &s.packP, &s.noff}) b->release();
+        for (DevBuf *b : {&s.text, &s.pattern, &s.toff, &s.poff, &s.results, &s.alnoff, &s.outT, &s.outP, &s.dirs, &s.fill, &s.order, &s.snap, &s.packT, &s.packP, &s.noff, &s.stats}) b->release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
         if (s.in) cudaEventDestroy(s.in);
@@ -1174,6 +1181,14 @@ int sa_last_timing(const sa_context *cctx, sa_timing *out)
 }
 
 int sa_last_cuda_error(const sa_context *ctx) { return ctx ? ctx->last_cuda : 0; }
+
+int sa_last_stats(sa_context *ctx, sa_stats *out)
+{
+    if (!ctx || !out) return SA_ERR_ARGUMENT;
+    if (!ctx->have_stats) return SA_ERR_ARGUMENT;        // no alignment with strings yet (or the last call was fill-only)
+    *out = ctx->last_stats;
+    return SA_OK;
+}
 
 void *sa_context_stream(const sa_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
@@ -1224,14 +1239,18 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
         SA_TRY(ctx->sortbuf.reserve(batch_sort_bytes(1)), SA_ERR_MEMORY);
         sa_batch b{1, ctx->dtext.as<uint8_t>(), d_offs, ctx->dpat.as<uint8_t>(), d_offs + 2};
         cudaEventRecord(ctx->ev[2], st);
-        rc = enqueue_batch(ctx, sc, &b, d_res, d_alnoff, ctx->doutT.as<char>(), ctx->doutP.as<char>(),
+        uint32_t *d_st = reinterpret_cast<uint32_t *>(ctx->misc.as<char>() + 192);
+        rc = enqueue_batch(ctx, sc, &b, d_res, d_alnoff, d_st, ctx->doutT.as<char>(), ctx->doutP.as<char>(),
                            (uint32_t)n, (uint32_t)m, ctx->dirs.as<uint32_t>(), ctx->dirs.cap / 4, ctx->fill.p,
                            ctx->sortbuf.p, &ctx->snapbuf, st, 0, 1);
         if (rc) return rc;
         cudaEventRecord(ctx->ev[3], st);
         SA_TRY(cudaMemcpyAsync(&hres, d_res, sizeof hres, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         SA_TRY(cudaMemcpyAsync(&hoff, d_alnoff, 8, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        uint32_t hst[2] = {0, 0};
+        SA_TRY(cudaMemcpyAsync(hst, d_st, 8, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);
+        ctx->last_stats.identity = hst[0]; ctx->last_stats.gaps = hst[1]; ctx->have_stats = traceback;
         if (sc->mode == SA_LOCAL) {
             uint32_t ij[2] = {0, 0};
             cudaMemcpy(&ij[0], reinterpret_cast<uint32_t *>(ctx->fill.p) + 1, 4, cudaMemcpyDeviceToHost);
@@ -1247,7 +1266,10 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
         uint64_t hr[4]; int32_t hs = 0;
         SA_TRY(cudaMemcpyAsync(hr, ctx->misc.p, sizeof hr, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         SA_TRY(cudaMemcpyAsync(&hs, ctx->misc.as<char>() + 32, 4, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        unsigned long long hst[2] = {0, 0};
+        if (traceback) SA_TRY(cudaMemcpyAsync(hst, ctx->stats_src, 16, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);
+        ctx->last_stats.identity = hst[0]; ctx->last_stats.gaps = hst[1]; ctx->have_stats = traceback;
         hres.score = hs; hres.aln_len = hr[0]; hres.start_text = hr[1]; hres.start_pattern = hr[2];
         hoff = slot - hr[0];
         hargmax = hr[3];
@@ -1581,7 +1603,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
         const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, b->n_pairs - first);
         const int k = pipeline ? (c & 1) : 0;
         if (pipeline && c >= 2) cudaStreamWaitEvent(st, ctx->evTrace[k], 0);      // buffer set k is free again
-        rc = enqueue_batch(ctx, sc, b, out->results, out->aln_off, out->aligned_text, out->aligned_pattern,
+        rc = enqueue_batch(ctx, sc, b, out->results, out->aln_off, out->stats, out->aligned_text, out->aligned_pattern,
                            max_n, max_m, ctx->pdirs[k].as<uint32_t>(), ctx->pdirs[k].cap / 4, ctx->fill.p, ctx->psort[k].p,
                            &ctx->snapbuf, st, (uint32_t)first, count, pipeline ? ctx->stream : nullptr,
                            pipeline ? ctx->evFill[k] : nullptr, pipeline && first + chunk < b->n_pairs);
@@ -1689,7 +1711,11 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             // 3/32, 2/32, 1/32 (SA_HOST_CHUNKS selects equal chunks instead).
             std::vector<uint64_t> bounds{0};
             if (!std::getenv("SA_HOST_CHUNKS") && N >= 65536 && chunk >= N / 8) {
+                // (fewer, larger chunks for smaller batches -- a chunk's fill should stay above ~1 ms, below that the class
+                // kernels' tails and the launch gaps show: 125 k pairs 5.95 -> 5.3 ms, 250 k pairs 10.1 -> 9.3 ms)
                 std::vector<int> w{1, 2, 3, 4, 4, 4, 4, 4, 3, 2, 1};
+                if (N < 200000) w = {2, 3, 3, 2};
+                else if (N < 400000) w = {1, 2, 3, 3, 3, 2, 1};
                 if (const char *e = std::getenv("SA_HOST_SCHEDULE")) {          // e.g. "1,2,4,5,5,5,5,3,2": parts of the batch
                     std::vector<int> u;
                     for (const char *q = e; *q;) { const int v = std::atoi(q); if (v > 0) u.push_back(v); while (*q && *q != ',') ++q; if (*q) ++q; }
@@ -1721,6 +1747,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 SA_TRY(s.outT.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
                 SA_TRY(s.outP.reserve(maxT + maxP + 16), SA_ERR_MEMORY);
                 SA_TRY(s.fill.reserve(chunk * 12 + 64), SA_ERR_MEMORY);
+                if (out->stats) SA_TRY(s.stats.reserve(chunk * 8 + 64), SA_ERR_MEMORY);
             }
             for (int k = 0; k < 2; ++k) {
                 SA_TRY(ctx->pdirs[k].reserve(batch_dirs_bound(T, chunk) * 4), SA_ERR_MEMORY);
@@ -1750,6 +1777,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 if (hostBase + total > out->arena_capacity) return SA_ERR_CAPACITY;
                 SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
                 SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                if (out->stats) { SA_TRY(cudaMemcpyAsync(out->stats + 2 * first, s.stats.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY); d2hBytes += count * 8; }
                 if (total) {
                     SA_TRY(cudaMemcpyAsync(out->aligned_text + hostBase, s.packT.p, total, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
                     SA_TRY(cudaMemcpyAsync(out->aligned_pattern + hostBase, s.packP.p, total, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
@@ -1778,8 +1806,8 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                 if (c >= 2) cudaStreamWaitEvent(stFill, ctx->evTrace[d], 0);  // direction set d is free again
                 sa_batch cb{count, s.text.as<uint8_t>() - tb, s.toff.as<int64_t>(), s.pattern.as<uint8_t>() - pb, s.poff.as<int64_t>()};
                 char *oT = s.outT.as<char>() - (tb + pb), *oP = s.outP.as<char>() - (tb + pb);
-                rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
-                                   ctx->pdirs[d].as<uint32_t>(), ctx->pdirs[d].cap / 4, s.fill.p, ctx->psort[d].p, &ctx->snapbuf,
+                rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), out->stats ? s.stats.as<uint32_t>() : nullptr,
+                                   oT, oP, max_n, max_m, ctx->pdirs[d].as<uint32_t>(), ctx->pdirs[d].cap / 4, s.fill.p, ctx->psort[d].p, &ctx->snapbuf,
                                    stFill, 0, (uint32_t)count, ctx->stream, ctx->evFill[d], /*tbShare=*/c + 1 < nChunk);
                 if (rc) return rc;
                 SA_TRY(cudaEventRecord(ctx->evTrace[d], ctx->stream), SA_ERR_LAUNCH);
@@ -1787,6 +1815,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                     cudaStreamWaitEvent(stOut, ctx->evTrace[d], 0);
                     SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
                     SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
+                    if (out->stats) { SA_TRY(cudaMemcpyAsync(out->stats + 2 * first, s.stats.p, count * 8, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY); d2hBytes += count * 8; }
                     SA_TRY(cudaMemcpyAsync(out->aligned_text + (tb - to[0]) + (pb - po[0]), s.outT.p, arena, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
                     SA_TRY(cudaMemcpyAsync(out->aligned_pattern + (tb - to[0]) + (pb - po[0]), s.outP.p, arena, cudaMemcpyDeviceToHost, stOut), SA_ERR_COPY);
                     SA_TRY(cudaEventRecord(s.out, stOut), SA_ERR_LAUNCH);
@@ -1832,6 +1861,7 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             SA_TRY(s.dirs.reserve(batch_dirs_bound(T, count) * 4), SA_ERR_MEMORY);
             SA_TRY(s.fill.reserve(count * 12 + 64), SA_ERR_MEMORY);
             SA_TRY(s.order.reserve(batch_sort_bytes(count)), SA_ERR_MEMORY);
+            if (out->stats) SA_TRY(s.stats.reserve(count * 8 + 64), SA_ERR_MEMORY);
             SA_TRY(cudaMemcpyAsync(s.text.p, b->text + tb, tbytes, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(s.pattern.p, b->pattern + pb, pbytes, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(s.toff.p, to + first, (count + 1) * 8, cudaMemcpyHostToDevice, s.stream), SA_ERR_COPY);
@@ -1844,12 +1874,13 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
             char *oT = s.outT.as<char>() - (tb + pb), *oP = s.outP.as<char>() - (tb + pb);
             // members too long for the batch kernels are skipped by the device-side classifier
             // (and aligned one by one below)
-            rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), oT, oP, max_n, max_m,
-                               s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, &s.snap, s.stream, 0, (uint32_t)count,
+            rc = enqueue_batch(ctx, sc, &cb, s.results.as<sa_result>(), s.alnoff.as<uint64_t>(), out->stats ? s.stats.as<uint32_t>() : nullptr,
+                               oT, oP, max_n, max_m, s.dirs.as<uint32_t>(), s.dirs.cap / 4, s.fill.p, s.order.p, &s.snap, s.stream, 0, (uint32_t)count,
                                nullptr, nullptr, /*tbShare=*/false);      // (measured: sharing does not pay with three slots in flight)
             if (rc) return rc;
             SA_TRY(cudaMemcpyAsync(out->results + first, s.results.p, count * sizeof(sa_result), cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(out->aln_off + first, s.alnoff.p, count * 8, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
+            if (out->stats) { SA_TRY(cudaMemcpyAsync(out->stats + 2 * first, s.stats.p, count * 8, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY); d2hBytes += count * 8; }
             SA_TRY(cudaMemcpyAsync(out->aligned_text + (tb - to[0]) + (pb - po[0]), s.outT.p, arena, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaMemcpyAsync(out->aligned_pattern + (tb - to[0]) + (pb - po[0]), s.outP.p, arena, cudaMemcpyDeviceToHost, s.stream), SA_ERR_COPY);
             SA_TRY(cudaEventRecord(s.done, s.stream), SA_ERR_LAUNCH);
@@ -1884,6 +1915,11 @@ int sa_align_batch(sa_context *ctx, const sa_scoring *sc, const sa_batch *b, sa_
                                out->aligned_text + slot, out->aligned_pattern + slot, n + m);
         if (r) return r;
         out->aln_off[p] = slot;
+        if (out->stats) {
+            sa_stats st{};
+            sa_last_stats(c, &st);
+            out->stats[2 * p] = (uint32_t)st.identity; out->stats[2 * p + 1] = (uint32_t)st.gaps;
+        }
         sa_last_timing(c, k);
         return SA_OK;
     };
@@ -2019,7 +2055,7 @@ int sa_align_batch_multi(const sa_options *opt, const sa_scoring *sc, const sa_b
         const uint64_t base = (uint64_t)(to[f] - to[0]) + (uint64_t)(po[f] - po[0]);
         sa_batch sb{cnt, b->text, to + f, b->pattern, po + f};
         sa_batch_out so{out->results + f, out->aln_off + f, out->aligned_text + base, out->aligned_pattern + base,
-                        (uint64_t)(to[f + cnt] - to[f]) + (uint64_t)(po[f + cnt] - po[f])};
+                        (uint64_t)(to[f + cnt] - to[f]) + (uint64_t)(po[f + cnt] - po[f]), out->stats ? out->stats + 2 * f : nullptr};
         sa_context *c = g_multi_ctx[opt->devices[k]];
         status[k] = sa_align_batch(c, sc, &sb, &so);
         if (status[k] == SA_OK) {

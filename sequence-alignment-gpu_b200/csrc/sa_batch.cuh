@@ -322,6 +322,9 @@ struct BatchTraceArgs {
     // outputs (per pair)
     sa_result *results;  uint64_t *aln_off;
     char *out_text;  char *out_pattern;
+    // optional (may be nullptr): per pair {identity, gaps} -- the two counts of prettyAlignmentPrint
+    // (utilities.cpp:262-283: columns with equal letters / columns with a gap), taken while the strings are emitted
+    uint32_t *stats;
 };
 
 __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceArgs A)
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
 
         int i = (int)A.end_i[pair], j = (int)A.end_j[pair];
         int H = A.local ? A.score[pair] : 0;       // global: accumulated along the path (the fill does not report it)
-        uint32_t len = 0;
+        uint32_t len = 0, nDiag = 0, nIdent = 0;
         uint32_t cachedIdx = ~0u, cachedWord = 0;
         // (lane, row-in-lane) of DP row i, kept incrementally: no integer division in the walk
         int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
@@ -427,6 +430,7 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
                 const int ct = rdT.get(ti), cp = rdP.get(pi);
                 emit(alphS[takeT ? ct : alpha], alphS[takeP ? cp : alpha]);
                 H += (tag == TAG_DIAG) ? (int)S8[cp * alpha + ct] : -gap;      // the path's score is H(m, n)
+                nDiag += (tag == TAG_DIAG); nIdent += (tag == TAG_DIAG && ct == cp);
                 ti = max(0, ti - (int)takeT);
                 pi = max(0, pi - (int)takeP);
                 if (takeP) row_up();
@@ -441,6 +445,7 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
                 const int ct = rdT.get(ti), cp = rdP.get(pi);      // ti == j-1 and pi == i-1 inside the matrix
                 emit(alphS[takeT ? ct : alpha], alphS[takeP ? cp : alpha]);
                 H += (tag == TAG_DIAG) ? -(int)S8[cp * alpha + ct] : gap;
+                nDiag += (tag == TAG_DIAG); nIdent += (tag == TAG_DIAG && ct == cp);
                 if (takeP) row_up();
                 j -= takeT;
                 if (i == 0 || j == 0) break;           // :45-46, before the index update
@@ -459,6 +464,7 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
         res.start_pattern = (uint64_t)(int64_t)pi;
         A.results[pair] = res;
         A.aln_off[pair] = slotEnd - len;
+        if (A.stats) { A.stats[2 * (size_t)pair] = nIdent; A.stats[2 * (size_t)pair + 1] = len - nDiag; }
     }
 }
 

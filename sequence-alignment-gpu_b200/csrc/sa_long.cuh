@@ -383,6 +383,7 @@ struct LongTraceArgs {
     char *out_text; char *out_pattern;
     uint64_t *res;           // [0]=len [1]=start_text [2]=start_pattern [3]=argmax linear index
     int emit;                // 0: score / arg-max only (the reference's BENCHMARK mode)
+    unsigned long long *stats;   // optional: {identity, gaps} of the emitted alignment
 };
 
 static __global__ void long_traceback_kernel(const LongTraceArgs A)
@@ -409,7 +410,7 @@ static __global__ void long_traceback_kernel(const LongTraceArgs A)
     if (!A.emit) { A.res[0] = 0; A.res[1] = 0; A.res[2] = 0; return; }
     const char GAPC = A.alphabet[A.alpha];
     char *oT = A.out_text + A.cap, *oP = A.out_pattern + A.cap;
-    uint64_t len = 0;
+    uint64_t len = 0, nIdent = 0, nGap = 0;
     size_t cachedAddr = ~(size_t)0; uint32_t cachedWord = 0;
     auto fetch = [&](int ii, int jj) -> int {
         const int s = (ii - 1) / ROWS, rr = (ii - 1) % ROWS;
@@ -428,6 +429,9 @@ static __global__ void long_traceback_kernel(const LongTraceArgs A)
         if (addr != cachedAddr) { cachedAddr = addr; cachedWord = A.dirs[addr]; }
         return (cachedWord >> (bit & 31)) & 3;
     };
+    auto count = [&](const bool takeT, const bool takeP, const int tIdx, const int pIdx) {
+        if (takeT && takeP) nIdent += A.text[tIdx] == A.pattern[pIdx]; else ++nGap;
+    };
     int ti, pi;
     if (!A.local) {
         ti = n - 1; pi = m - 1;
@@ -440,6 +444,7 @@ static __global__ void long_traceback_kernel(const LongTraceArgs A)
             ++len;
             oT[-(int64_t)len] = takeT ? A.alphabet[A.text[ti]] : GAPC;
             oP[-(int64_t)len] = takeP ? A.alphabet[A.pattern[pi]] : GAPC;
+            count(takeT, takeP, ti, pi);
             ti = max(0, ti - (int)takeT);
             pi = max(0, pi - (int)takeP);
             i -= takeP; j -= takeT;
@@ -452,6 +457,7 @@ static __global__ void long_traceback_kernel(const LongTraceArgs A)
             ++len;
             oT[-(int64_t)len] = takeT ? A.alphabet[A.text[ti]] : GAPC;
             oP[-(int64_t)len] = takeP ? A.alphabet[A.pattern[pi]] : GAPC;
+            count(takeT, takeP, ti, pi);
             if (tag == TAG_DIAG) H -= A.S[A.pattern[i - 1] * A.alpha + A.text[j - 1]]; else H += A.gap;
             i -= takeP; j -= takeT;
             if (i == 0 || j == 0) break;
@@ -462,6 +468,7 @@ static __global__ void long_traceback_kernel(const LongTraceArgs A)
     A.res[0] = len;
     A.res[1] = (uint64_t)(int64_t)ti;
     A.res[2] = (uint64_t)(int64_t)pi;
+    if (A.stats) { A.stats[0] = nIdent; A.stats[1] = nGap; }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -42,6 +42,8 @@ struct TbState {            // device-resident scalars of one traceback
     int exit_row;           // column slices: DP row at which the path leaves through the slice's left edge
     unsigned long long total_len;
     unsigned long long fallbacks;   // segments resolved by the serial fallback (diagnostic)
+    // the two counts of prettyAlignmentPrint (utilities.cpp:262-283), accumulated by the emitting segments
+    unsigned long long identity, gaps;
 };
 
 struct TbArgs {
@@ -154,6 +156,8 @@ __global__ void tb_prepare_kernel(const TbArgs A)
     A.st->cut_seg = -1;
     A.st->total_len = 0;
     A.st->fallbacks = 0;
+    A.st->identity = 0;
+    A.st->gaps = 0;
 }
 
 // First candidate index of line s: the band is centred on the straight-line prediction of the
@@ -227,7 +231,7 @@ __device__ __forceinline__ void tb_segment(const TbArgs &A, const int t)
     int j = (t == s0) ? A.st->j0 : A.X[t + 1];
     const int stop_row = t * L.ROWS;
     TbCursor cur;
-    unsigned long long len = 0;
+    unsigned long long len = 0, nIdent = 0, nGap = 0;
     long long delta = 0, dmin = 0;
     long long budget = 0;                       // MODE 1, local: steps this segment may still emit
     unsigned long long off = 0;
@@ -258,10 +262,15 @@ __device__ __forceinline__ void tb_segment(const TbArgs &A, const int t)
             const unsigned long long pos = off + len + 1;
             oT[-(long long)pos] = takeT ? A.alphabet[A.text[j - 1]] : GAPC;
             oP[-(long long)pos] = takeP ? A.alphabet[A.pattern[i - 1]] : GAPC;
+            if (takeT && takeP) nIdent += A.text[j - 1] == A.pattern[i - 1]; else ++nGap;
             if (budget > 0) --budget;
         }
         ++len;
         i -= takeP; j -= takeT;
+    }
+    if (MODE == 1 && len) {
+        atomicAdd(&A.st->identity, nIdent);
+        atomicAdd(&A.st->gaps, nGap);
     }
     if (MODE == 0) {
         A.seg_len[t] = len;

@@ -751,3 +751,43 @@ def test_tile_kernel_many_strips_in_waves(aligner, oracle, force_path, monkeypat
         s, _ = oracle.score_only(mode, 23, b62, 5, t, p)
         assert got.score == s
         assert oracle.rescore(got.aligned_text, got.aligned_pattern, 23, b62, 5) == got.score
+
+
+def test_device_side_identity_and_gap_counts(sa, aligner, oracle, force_path, monkeypatch):
+    """the two counts of prettyAlignmentPrint (utilities.cpp:262-283) come from the device, taken while the
+    strings are emitted: sa_last_stats for single pairs (batch kernels, tiled and one-column long-pair kernels, serial
+    traceback) and sa_batch_out.stats for batches -- equal to a host pass over the emitted strings."""
+    rng = np.random.default_rng(8)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+
+    def counts(a):
+        at, ap = np.frombuffer(a.aligned_text, np.uint8), np.frombuffer(a.aligned_pattern, np.uint8)
+        return int((at == ap).sum()), int(((at == 45) | (ap == 45)).sum())
+
+    for path, env in (("batch", {}), ("long", {}), ("long", {"SA_LONG_KERNEL": "strip"}), ("long", {"SA_TB": "serial"}), ("long", {"SA_TILE": "4,4"})):
+        force_path(path)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for it in range(6):
+            alpha, mat = (4, blast) if it % 2 == 0 else (23, b62)
+            t, p = helpers.random_case(rng, alpha, n_max=[60, 300, 1500][it % 3] if path == "long" else 300, similar=it % 3 != 2)
+            for mode in (0, 1):
+                a = aligner.align(mode, alpha, mat, 3, t, p)
+                assert_same(a, oracle.align(mode, alpha, mat, 3, t, p), (path, env, it, mode))
+                if a.aln_len:
+                    assert aligner.last_stats() == counts(a), (path, env, it, mode)
+        for k in env:
+            monkeypatch.delenv(k)
+    force_path(None)
+    import synth
+    for N in (500, 9000):                  # the slot pipeline and the staged, packed pipeline
+        T, toff, P, poff = synth.synthetic_batch(N, seed=77, lo=40, hi=300)
+        arena = int(toff[-1] + poff[-1])
+        out = dict(results=np.zeros(N, sa.RESULT_DTYPE), aln_off=np.zeros(N, np.uint64), aligned_text=np.empty(arena, np.uint8),
+                   aligned_pattern=np.empty(arena, np.uint8), stats=np.full(2 * N, 0xffffffff, np.uint32))
+        for mode in (1, 0):
+            aligner.align_batch(mode, 23, b62, 5, T, toff, P, poff, out=out)
+            for i in list(range(0, N, 97)) + [N - 1]:
+                a = sa.unpack_batch(out, i)
+                assert (int(out["stats"][2 * i]), int(out["stats"][2 * i + 1])) == counts(a), (N, mode, i)

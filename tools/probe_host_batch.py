@@ -21,7 +21,9 @@ out = dict(results=torch.zeros(N * 4, dtype=torch.int64).pin_memory().numpy().vi
            aligned_text=torch.empty(arena, dtype=torch.uint8).pin_memory().numpy(),
            aligned_pattern=torch.empty(arena, dtype=torch.uint8).pin_memory().numpy())
 al = sa.Aligner(0)
-for env in ({}, {"SA_HOST_IOSETS": "3"}, {"SA_HOST_IOSETS": "5"}, {"SA_HOST_SCHEDULE": "1,2,4,5,5,5,5,3,2"},
+SCHED = os.environ.get("SCHEDULES")
+envs = [{}] + [{"SA_HOST_SCHEDULE": x} for x in SCHED.split(";")] if SCHED else None
+for env in envs or ({}, {"SA_HOST_IOSETS": "3"}, {"SA_HOST_IOSETS": "5"}, {"SA_HOST_SCHEDULE": "1,2,4,5,5,5,5,3,2"},
             {"SA_HOST_SCHEDULE": "1,2,3,3,3,3,3,3,3,3,2,2,1"}, {"SA_HOST_SCHEDULE": "1,2,4,6,6,6,4,2,1", "SA_HOST_IOSETS": "5"}):
     os.environ.update(env)
     a2 = al

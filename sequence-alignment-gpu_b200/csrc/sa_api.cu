@@ -86,6 +86,7 @@ struct sa_context {
     DevBuf dS4, dS;
     // single-pair / device-batch workspaces
     DevBuf dirs, rowbuf, fill, misc, dtext, dpat, doutT, doutP, sortbuf, tbbuf, snapbuf;
+    DevBuf ckpt;                          // checkpoint rows of the linear-space traceback
     // device-batch pipeline: fills on the caller's stream, tracebacks on `stream`, two buffer sets
     DevBuf pdirs[2], psort[2];
     DevBuf packstate;                     // staged host path: running total of the packed strings
@@ -769,6 +770,21 @@ struct LongPlan {
     size_t strip_stride, row_stride, smem;
 };
 
+// Resident blocks per SM of a tiled fill.  The strips form a chain in which strip s+1 runs one hand-off lag (~55 macro-steps,
+// see DESIGN.md 4.2) behind strip s, so only (macro-steps of a sweep) / 55 strips can be busy at a time; warps beyond that
+// only slow the busy ones down -- the lag, which every one of the n_strips pays, is a number of macro-steps.  Measured on a
+// 125 000-column slice of config 5 (3716 strips): 76.8 / 57.0 / 63.5 / 72.6 ms with 1 / 2 / 3 / 4 blocks per SM, and strip 0
+// crosses the slice in 9.5 / 11.8 / 13.7 / 14.8 ms (the delay per GPU of the linked slices).  SA_LONG_BLOCKS_PER_SM overrides.
+int tile_blocks_per_sm(const sa_context *ctx, uint64_t n, int C, int occ)
+{
+    int perSm = std::min(occ, 8);
+    const uint64_t busy = (n / (uint64_t)C + 31) / 55 + 1;
+    const uint64_t perBlockSm = (uint64_t)ctx->sms * TILE_WARPS;
+    perSm = (int)std::min<uint64_t>((uint64_t)perSm, std::max<uint64_t>(1, (busy + perBlockSm - 1) / perBlockSm));
+    if (const char *e = std::getenv("SA_LONG_BLOCKS_PER_SM")) { const int b = std::atoi(e); if (b >= 1) perSm = std::min(occ, b); }
+    return perSm;
+}
+
 // Which long-pair kernel, measured on B200 (tools/probe_tile.py, profiles/README.md round 2).  The register-tiled kernel
 // (sa_tile.cuh) is built for the latency-bound regime -- at most a few strips per SM scheduler, i.e. up to ~300 k rows:
 // 100 000 x 95 217 fills in 10.3 ms with 8 x 2 tiles against 13.7 ms (one-column kernel), 4 000 x 3 800 in 0.41 against
@@ -840,7 +856,8 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
         const int occ = tile_occupancy(tR, tC, local, linked, P->smem);
         if (occ < 1) return SA_ERR_LAUNCH;
         // every strip of a launch should be resident at once when it can be: up to 8 blocks (32 strips) per SM
-        const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 8);
+        const int perSm = tile_blocks_per_sm(ctx, n, tC, occ);
+        const uint64_t maxBlocks = (uint64_t)ctx->sms * perSm;
         const uint64_t needBlocks = (P->n_strips + TILE_WARPS - 1) / TILE_WARPS;
         P->grid = (int)std::min(maxBlocks, needBlocks);
         const uint64_t W = (uint64_t)P->grid * TILE_WARPS;
@@ -856,7 +873,9 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
     P->smem = planes * 32 * MAX_ALPHA + (size_t)LONG_WARPS * (planes * (size_t)sc->alphabet_size * 32 * rpad_for(R) + (local ? ((R + 3) / 4) * 32 * 16 : 0) + 64 + 2 * PB * 4);
     int occ = occupancy_long(R, local, P->smem, false, wide);
     if (occ < 1) return SA_ERR_LAUNCH;
-    const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, 2);
+    int perSm = std::min(occ, 2);
+    if (const char *e = std::getenv("SA_LONG_BLOCKS_PER_SM")) { const int b = std::atoi(e); if (b >= 1) perSm = std::min(occ, b); }
+    const uint64_t maxBlocks = (uint64_t)ctx->sms * perSm;
     const uint64_t needBlocks = (P->n_strips + LONG_WARPS - 1) / LONG_WARPS;
     P->grid = (int)std::min(maxBlocks, needBlocks);
     const uint64_t W = (uint64_t)P->grid * LONG_WARPS;
@@ -869,10 +888,17 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
 
 // Parallel traceback over the strip layout of the last fill (sa_traceback.cuh).  start_row >= 0 selects the
 // column-slice form: the path starts at (start_row, n) and, with `slice`, ends on the slice's left edge.
+__global__ void tb_stats_accumulate_kernel(const unsigned long long *src, unsigned long long *dst) { dst[0] += src[0]; dst[1] += src[1]; }
+__global__ void tb_finish_checkpointed_kernel(uint64_t *res, const unsigned long long *emitted) { res[0] = *emitted; res[1] = 0; res[2] = 0; res[3] = 0; }
+
+struct TbChunk {          // row chunk of a checkpointed traceback (see TbArgs)
+    const int *start_col_dev = nullptr; bool chunk_top = false; unsigned long long *global_off = nullptr; int *exit_col_dev = nullptr;
+};
 int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, uint64_t m, const uint8_t *d_text,
                                const uint8_t *d_pat, int alpha, int gap, const char *alphabet, bool local, int *d_cv,
                                uint32_t *d_ci, uint32_t *d_cj, int32_t *d_score, char *d_outT, char *d_outP, uint64_t cap,
-                               uint64_t *d_res, bool traceback, long long start_row, bool slice, double slope, cudaStream_t st)
+                               uint64_t *d_res, bool traceback, long long start_row, bool slice, double slope, cudaStream_t st,
+                               const TbChunk *chunk = nullptr)
 {
     {
         TbArgs T{};
@@ -905,6 +931,7 @@ int enqueue_parallel_traceback(sa_context *ctx, const LongPlan &P, uint64_t n, u
             T.slope = slope > 0 ? slope : local ? 1.0 : (double)n / (double)m;
         }
         T.cand_v = d_cv; T.cand_i = d_ci; T.cand_j = d_cj; T.score = d_score;
+        if (chunk) { T.start_col_dev = chunk->start_col_dev; T.chunk_top = chunk->chunk_top ? 1 : 0; T.global_off = chunk->global_off; T.exit_col_dev = chunk->exit_col_dev; }
         const size_t nq = (size_t)2 * T.BQ + 1, S = P.n_strips;
         size_t off = 0;
         auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -1009,6 +1036,137 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
     cudaEventRecord(e3, st);
     ctx->timing_dirty = true;
     return SA_OK;
+}
+
+// One GLOBAL alignment whose packed direction matrix does not fit the device (or SA_CKPT_ROWS asks for it): linear-space
+// traceback by checkpoints (the reference caps the matrix at host RAM, alignSequenceGPU.cu:410-416).
+//   pass 1  the matrix is filled in row chunks of `chunk` rows; only the int32 H row between two chunks is kept
+//           (n x 4 B per checkpoint), the direction words of a chunk are overwritten by the next one;
+//   pass 2  from the last chunk upwards: the chunk is filled again from its checkpoint (the last one still holds its
+//           directions), the path is followed from where the chunk below was left to the chunk's top row, and the
+//           piece is emitted in front of what has been emitted so far.
+// Twice the fill work, directions for ONE chunk in memory: 1 M x 0.95 M needs 16 GB at 64 k rows instead of 250 GB.
+// Everything is enqueued on `st` without a host synchronisation.  Results land where enqueue_long puts them.
+int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, const uint8_t *d_pat,
+                              uint64_t m, char *d_outT, char *d_outP, uint64_t cap, uint64_t chunk_hint, cudaStream_t st)
+{
+    if (sc->mode != SA_GLOBAL) return SA_ERR_MEMORY;
+    LongPlan P;
+    int rc = plan_long(ctx, sc, n, std::min<uint64_t>(m, chunk_hint), &P, true);
+    if (rc) return rc;
+    const uint64_t ROWS = 32ull * P.R;
+    const uint64_t chunk = std::min<uint64_t>((chunk_hint + ROWS - 1) / ROWS * ROWS, (m + ROWS - 1) / ROWS * ROWS);
+    const uint64_t K = (m + chunk - 1) / chunk;
+    const uint32_t stripsPerChunk = (uint32_t)(chunk / ROWS);
+    SA_TRY(ctx->dirs.reserve((size_t)stripsPerChunk * P.strip_stride * 4), SA_ERR_MEMORY);
+    SA_TRY(ctx->ckpt.reserve((size_t)K * n * 4 + 64), SA_ERR_MEMORY);
+    SA_TRY(ctx->misc.reserve(256), SA_ERR_MEMORY);
+    uint64_t *d_res = ctx->misc.as<uint64_t>();
+    int32_t *d_score = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 32);
+    int *d_col = reinterpret_cast<int *>(ctx->misc.as<char>() + 64);
+    unsigned long long *d_emitted = reinterpret_cast<unsigned long long *>(ctx->misc.as<char>() + 72);
+    unsigned long long *d_stats = reinterpret_cast<unsigned long long *>(ctx->misc.as<char>() + 80);      // identity, gaps over all chunks
+    const int ncol = (int)n;
+    SA_TRY(cudaMemcpyAsync(d_col, &ncol, 4, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
+    SA_TRY(cudaMemsetAsync(d_emitted, 0, 24, st), SA_ERR_LAUNCH);
+    auto ckrow = [&](uint64_t c) { return ctx->ckpt.as<int>() + (size_t)c * n; };          // top row of chunk c (c >= 1)
+    int32_t *d_scratch_score = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 100);   // pass 2: a chunk's own corner value is not the score
+    auto fill_chunk = [&](uint64_t c, bool keepBottom) -> int {
+        const uint64_t row0 = c * chunk, rows = std::min<uint64_t>(chunk, m - row0);
+        const uint32_t nStrips = (uint32_t)((rows + ROWS - 1) / ROWS);
+        const int grid = (int)std::min<uint64_t>((uint64_t)P.grid, (nStrips + LONG_WARPS - 1) / LONG_WARPS);
+        const uint32_t ring = (uint32_t)std::min<uint64_t>(nStrips, (uint64_t)grid * LONG_WARPS + 1);
+        const size_t rowEntries = (size_t)ring * P.row_stride;
+        const bool fresh = rowEntries * 8 > ctx->rowbuf.cap;
+        if (fresh) SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);
+        SA_TRY(ctx->rowbuf.reserve(rowEntries * 8), SA_ERR_MEMORY);
+        ctx->epoch = (ctx->epoch + 1) & 0x7ff;
+        if (fresh || ctx->epoch == 0) {
+            SA_TRY(cudaMemsetAsync(ctx->rowbuf.p, 0, ctx->rowbuf.cap, st), SA_ERR_LAUNCH);
+            if (ctx->epoch == 0) ctx->epoch = 1;
+        }
+        LongArgs A{};
+        A.text = d_text; A.n = (uint32_t)n; A.pattern = d_pat + row0; A.m = (uint32_t)rows;
+        A.dirs = ctx->dirs.as<uint32_t>(); A.strip_stride = P.strip_stride;
+        A.rowbuf = ctx->rowbuf.as<unsigned long long>(); A.ring = ring; A.row_stride = P.row_stride;
+        A.S4 = ctx->dS4.as<int8_t>(); A.alpha = sc->alphabet_size; A.gap = sc->gap;
+        A.n_strips = nStrips; A.col0 = 0; A.row_base = (uint32_t)row0;
+        A.top_row = c ? ckrow(c) : nullptr;
+        A.bottom_row = (keepBottom && c + 1 < K) ? ckrow(c + 1) : nullptr;
+        A.score = keepBottom ? d_score : d_scratch_score;
+        A.tag_base = (uint32_t)ctx->epoch << 21;
+        A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
+        SA_TRY(launch_plan(P, A, false, grid, st, ctx->wide), SA_ERR_LAUNCH);
+        ctx->timing.kernel_launches++;
+        if (A.bottom_row) {
+            const unsigned long long *row = A.rowbuf + (size_t)((nStrips - 1) % ring) * P.row_stride;
+            long_bottom_row_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row, A.bottom_row, (uint32_t)n);
+            SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+            ctx->timing.kernel_launches++;
+        }
+        return SA_OK;
+    };
+    cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
+    cudaEventRecord(e0, st);
+    for (uint64_t c = 0; c < K; ++c) { rc = fill_chunk(c, true); if (rc) return rc; }
+    cudaEventRecord(e1, st);
+    cudaEventRecord(e2, st);          // (the second pass interleaves fills and tracebacks: it is accounted as traceback time)
+    for (uint64_t c = K; c-- > 0;) {
+        if (c + 1 < K) { rc = fill_chunk(c, false); if (rc) return rc; }
+        const uint64_t row0 = c * chunk, rows = std::min<uint64_t>(chunk, m - row0);
+        LongPlan Pc = P;
+        Pc.n_strips = (uint32_t)((rows + ROWS - 1) / ROWS);
+        TbChunk tc;
+        tc.start_col_dev = d_col; tc.chunk_top = c > 0; tc.global_off = d_emitted; tc.exit_col_dev = d_col;
+        rc = enqueue_parallel_traceback(ctx, Pc, n, rows, d_text, d_pat + row0, sc->alphabet_size, sc->gap, sc->alphabet, false, nullptr,
+                                        nullptr, nullptr, nullptr, d_outT, d_outP, cap, d_res, true, (long long)rows, false,
+                                        (double)n / (double)m, st, &tc);
+        if (rc) return rc;
+        tb_stats_accumulate_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const unsigned long long *>(ctx->stats_src), d_stats);
+        ctx->timing.kernel_launches++;
+    }
+    // results in the layout of enqueue_long: {len, start_text, start_pattern, argmax} -- a global alignment starts at 0 / 0
+    tb_finish_checkpointed_kernel<<<1, 1, 0, st>>>(d_res, d_emitted);
+    SA_TRY(cudaGetLastError(), SA_ERR_LAUNCH);
+    ctx->stats_src = d_stats;
+    cudaEventRecord(e3, st);
+    ctx->timing_dirty = true;
+    return SA_OK;
+}
+
+// When the packed directions of a GLOBAL alignment would not fit the device (or SA_CKPT_ROWS forces it), the pair takes the
+// checkpointed path.  SA_CKPT_LIMIT_MB: direction bytes above which it is taken (default 60 % of the device memory);
+// SA_CKPT_CHUNK_MB: direction bytes of one row chunk (default 16 GB: 65 536 rows of a 1 000 000-column matrix).
+bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, bool traceback, uint64_t *chunk_rows)
+{
+    if (!traceback || sc->mode != SA_GLOBAL || ctx->wide) return false;
+    if (const char *e = std::getenv("SA_CKPT_ROWS")) {
+        const long long r = std::atoll(e);
+        if (r > 0 && (uint64_t)r < m) { *chunk_rows = (uint64_t)r; return true; }
+        return false;
+    }
+    const long double dirBytes = (long double)(n + 64) * (long double)(m + 512) / 4.0L;
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) { cudaGetLastError(); return false; }
+    long double limit = 0.6L * (long double)totalB;
+    if (const char *e = std::getenv("SA_CKPT_LIMIT_MB")) limit = (long double)std::atoll(e) * 1048576.0L;
+    if (dirBytes <= limit) return false;
+    long double chunkBytes = 16.0L * 1073741824.0L;
+    if (const char *e = std::getenv("SA_CKPT_CHUNK_MB")) chunkBytes = (long double)std::atoll(e) * 1048576.0L;
+    chunkBytes = std::min(chunkBytes, limit);
+    const uint64_t rows = (uint64_t)(chunkBytes * 4.0L / (long double)(n + 64));
+    *chunk_rows = std::max<uint64_t>(1024, rows);
+    return *chunk_rows < m;
+}
+
+// enqueue_long, or its checkpointed form when the direction matrix is too large for the device
+int enqueue_long_auto(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, const uint8_t *d_pat, uint64_t m,
+                      char *d_outT, char *d_outP, uint64_t cap, bool traceback, cudaStream_t st)
+{
+    uint64_t chunkRows = 0;
+    if (want_checkpoints(ctx, sc, n, m, traceback, &chunkRows))
+        return enqueue_long_checkpointed(ctx, sc, d_text, n, d_pat, m, d_outT, d_outP, cap, chunkRows, st);
+    return enqueue_long(ctx, sc, d_text, n, d_pat, m, d_outT, d_outP, cap, traceback, st);
 }
 
 // members of a batch that the batch kernels can take (the device-side classifier applies the same rule)
@@ -1131,7 +1289,7 @@ void sa_destroy(sa_context *ctx)
     ctx->workers.clear();
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf, &ctx->tbbuf, &ctx->snapbuf})
+    for (DevBuf *b : {&ctx->dS4, &ctx->dS, &ctx->dirs, &ctx->rowbuf, &ctx->fill, &ctx->misc, &ctx->dtext, &ctx->dpat, &ctx->doutT, &ctx->doutP, &ctx->sortbuf, &ctx->tbbuf, &ctx->snapbuf, &ctx->ckpt})
         b->release();
     ctx->pin.release();
     for (auto &s : ctx->slot) {
@@ -1259,8 +1417,8 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
         }
     } else {
         cudaEventRecord(ctx->ev[2], st);
-        rc = enqueue_long(ctx, sc, ctx->dtext.as<uint8_t>(), n, ctx->dpat.as<uint8_t>(), m,
-                          ctx->doutT.as<char>(), ctx->doutP.as<char>(), slot, traceback, st);
+        rc = enqueue_long_auto(ctx, sc, ctx->dtext.as<uint8_t>(), n, ctx->dpat.as<uint8_t>(), m,
+                               ctx->doutT.as<char>(), ctx->doutP.as<char>(), slot, traceback, st);
         if (rc) return rc;
         cudaEventRecord(ctx->ev[3], st);
         uint64_t hr[4]; int32_t hs = 0;
@@ -1328,7 +1486,7 @@ int sa_align_device(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text
     if (rc) return rc;
     reset_timing(ctx);
     ctx->timing.cells = (n + 1) * (m + 1);
-    rc = enqueue_long(ctx, sc, d_text, n, d_pattern, m, d_outT, d_outP, n + m, true, st);
+    rc = enqueue_long_auto(ctx, sc, d_text, n, d_pattern, m, d_outT, d_outP, n + m, true, st);
     if (rc) return rc;
     // misc = {len, start_text, start_pattern, argmax} then score at byte 32
     SA_TRY(cudaMemcpyAsync(d_result4, ctx->misc.p, 24, cudaMemcpyDeviceToDevice, st), SA_ERR_COPY);
@@ -1476,7 +1634,10 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     const bool linkedKernel = d_left64 || d_right64 || std::getenv("SA_LONG_DBG");
     int occ = S.C ? tile_occupancy(S.R, S.C, false, linkedKernel, S.smem) : occupancy_long(S.R, false, S.smem, linkedKernel);
     if (occ < 1) return SA_ERR_LAUNCH;
-    const uint64_t maxBlocks = (uint64_t)ctx->sms * std::min(occ, S.C ? 8 : 2);
+    int perSm = std::min(occ, 2);
+    if (S.C) perSm = tile_blocks_per_sm(ctx, S.n, S.C, occ);
+    else if (const char *e = std::getenv("SA_LONG_BLOCKS_PER_SM")) { const int b = std::atoi(e); if (b >= 1) perSm = std::min(occ, b); }
+    const uint64_t maxBlocks = (uint64_t)ctx->sms * perSm;
     const int grid = (int)std::min<uint64_t>(maxBlocks, (nStrips + LONG_WARPS - 1) / LONG_WARPS);
     const uint32_t ring = (uint32_t)std::min<uint64_t>(nStrips, (uint64_t)grid * LONG_WARPS + 1);
     const size_t rowEntries = (size_t)ring * S.row_stride;

@@ -119,6 +119,62 @@ __host__ __device__ constexpr Sw16Layout sw16_layout(int R, int alpha, uint32_t 
     return Sw16Layout{wb, (uint32_t)warps * wb, 0u};
 }
 
+
+// Query profile of one pair, built by the lane that owns the rows: byte [a*PS + lane*RPAD + r] = 4*S[p_(lane*R+r)][a].
+// The lane reads the 4*S row of each of its R pattern letters four text letters at a time (one aligned word of the
+// 32-byte table row, L1-resident), transposes 4 rows x 4 letters with eight PRMTs and stores one word per letter:
+// R loads + 8*NPW PRMTs + 4*NPW stores per four letters instead of a byte load and a byte store per (row, letter).
+// Rows past the end of the pattern read as 0x80 (-128, the sentinel).  `prof` points at the lane's own RPAD bytes.
+template <int R>
+__device__ __forceinline__ void build_profile_rows(unsigned char *prof, const uint8_t *pt, const int m, const int l, const int alpha,
+                                                   const int8_t *S4)
+{
+    constexpr int RPAD = rpad_for(R);
+    constexpr int PS = 32 * RPAD;
+    constexpr int NPW = (R + 3) / 4;
+    const uint32_t *S4w = reinterpret_cast<const uint32_t *>(S4);
+    uint32_t rowoff[R];                 // word offset of the letter's table row, ~0u past the end of the pattern
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = l * R + r;
+        rowoff[r] = i < m ? 8u * (uint32_t)min((int)pt[i], alpha - 1) : ~0u;
+    }
+    const int na4 = (alpha + 3) >> 2;
+#pragma unroll 1
+    for (int a4 = 0; a4 < na4; ++a4) {
+        uint32_t W[4 * NPW];
+#pragma unroll
+        for (int r = 0; r < 4 * NPW; ++r) W[r] = 0x80808080u;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (rowoff[r] != ~0u) W[r] = __ldg(S4w + rowoff[r] + a4);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(prof + (size_t)(4 * a4) * PS);
+        const int left = alpha - 4 * a4;            // letters of this group that exist (1..4 in the last group)
+#pragma unroll
+        for (int q = 0; q < NPW; ++q) {
+            const uint32_t t0 = __byte_perm(W[4 * q], W[4 * q + 1], 0x5140), t1 = __byte_perm(W[4 * q + 2], W[4 * q + 3], 0x5140);
+            const uint32_t t2 = __byte_perm(W[4 * q], W[4 * q + 1], 0x7362), t3 = __byte_perm(W[4 * q + 2], W[4 * q + 3], 0x7362);
+            dst[q] = __byte_perm(t0, t1, 0x5410);
+            if (left > 1) dst[PS / 4 + q] = __byte_perm(t0, t1, 0x7632);
+            if (left > 2) dst[2 * (PS / 4) + q] = __byte_perm(t2, t3, 0x5410);
+            if (left > 3) dst[3 * (PS / 4) + q] = __byte_perm(t2, t3, 0x7632);
+        }
+    }
+}
+
+// What a task needs to know about one of its two pairs; loaded one task ahead of its use.
+struct PairMeta { uint32_t pair; int n, m; int64_t t0, p0; };
+__device__ __forceinline__ PairMeta load_pair_meta(const BatchArgs &A, const uint32_t pair, const bool valid)
+{
+    PairMeta M; M.pair = pair; M.n = 0; M.m = 0; M.t0 = 0; M.p0 = 0;
+    if (valid) {
+        M.t0 = A.text_off[pair]; M.p0 = A.pattern_off[pair];
+        M.n = (int)(A.text_off[pair + 1] - M.t0); M.m = (int)(A.pattern_off[pair + 1] - M.p0);
+    }
+    return M;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int R, bool LOCAL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArgs A)
 {
@@ -159,23 +215,27 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
     const int phase = (TPAD - l) & 3;                 // byte phase of the lane's column inside a text word
     const int word0 = (TPAD - l) >> 2;                // word that holds the lane's column at step 0
 
-    for (uint32_t task = blockIdx.x * WARPS + warp; task < nTasks; task += gridDim.x * WARPS) {
-        const uint32_t posA = task * 2, posB = posA + 1;
-        const bool validB = posB < n_pos;
-        uint32_t pairA = 0, pairB = 0; int nA = 0, mA = 0, nB = 0, mB = 0;
-        const uint8_t *txA = nullptr, *ptA = nullptr, *txB = nullptr, *ptB = nullptr;
+    // Task metadata runs ahead of its use so that the dependent loads (order -> offsets -> residues) of a task are
+    // not paid when it starts: the pair indices two tasks ahead, the offsets one task ahead, and the next task's
+    // residues are pulled into L2 while this task's matrix is filled.
+    const uint32_t taskStride = gridDim.x * WARPS;
+    const uint32_t task0 = blockIdx.x * WARPS + warp;
+    auto order_at = [&](const uint32_t pos) -> uint32_t { return pos < n_pos ? A.order[first_pos + pos] : 0u; };
+    uint32_t ordA = order_at(task0 * 2), ordB = order_at(task0 * 2 + 1);
+    PairMeta nextA = load_pair_meta(A, ordA, task0 * 2 < n_pos), nextB = load_pair_meta(A, ordB, task0 * 2 + 1 < n_pos);
+    ordA = order_at((task0 + taskStride) * 2); ordB = order_at((task0 + taskStride) * 2 + 1);
+
+    for (uint32_t task = task0; task < nTasks; task += taskStride) {
+        const PairMeta MA = nextA, MB = nextB;
         {
-            pairA = A.order[first_pos + posA];
-            const int64_t t0 = A.text_off[pairA], p0 = A.pattern_off[pairA];
-            nA = (int)(A.text_off[pairA + 1] - t0); mA = (int)(A.pattern_off[pairA + 1] - p0);
-            txA = A.text + t0; ptA = A.pattern + p0;
+            const uint32_t t1 = task + taskStride, t2 = t1 + taskStride;
+            nextA = load_pair_meta(A, ordA, t1 * 2 < n_pos); nextB = load_pair_meta(A, ordB, t1 * 2 + 1 < n_pos);
+            ordA = order_at(t2 * 2); ordB = order_at(t2 * 2 + 1);
         }
-        if (validB) {
-            pairB = A.order[first_pos + posB];
-            const int64_t t0 = A.text_off[pairB], p0 = A.pattern_off[pairB];
-            nB = (int)(A.text_off[pairB + 1] - t0); mB = (int)(A.pattern_off[pairB + 1] - p0);
-            txB = A.text + t0; ptB = A.pattern + p0;
-        }
+        const bool validB = task * 2 + 1 < n_pos;
+        const uint32_t pairA = MA.pair, pairB = MB.pair;
+        const int nA = MA.n, mA = MA.m, nB = MB.n, mB = MB.m;
+        const uint8_t *txA = A.text + MA.t0, *ptA = A.pattern + MA.p0, *txB = A.text + MB.t0, *ptB = A.pattern + MB.p0;
         __syncwarp();
         const int nG = max(nA, nB);
         const int nSteps = nG + 31;
@@ -186,14 +246,14 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
             textA[j] = (t >= 0 && t < nA) ? (unsigned char)min((int)txA[t], alpha - 1) : (unsigned char)sentA;
             textB[j] = (t >= 0 && t < nB) ? (unsigned char)min((int)txB[t], alpha - 1) : (unsigned char)sentB;
         }
-        for (int i = l; i < 32 * R; i += 32) {
-            const int off = (i / R) * RPAD + (i % R);
-            const int8_t *sa_ = i < mA ? S4s + 32 * min((int)ptA[i], alpha - 1) : nullptr;
-            const int8_t *sb_ = i < mB ? S4s + 32 * min((int)ptB[i], alpha - 1) : nullptr;
-            for (int a = 0; a < alpha; ++a) {
-                profA[a * PS + off] = sa_ ? (unsigned char)sa_[a] : (unsigned char)0x80;
-                profB[a * PS + off] = sb_ ? (unsigned char)sb_[a] : (unsigned char)0x80;
-            }
+        build_profile_rows<R>(profA + l * RPAD, ptA, mA, l, alpha, S4s);
+        build_profile_rows<R>(profB + l * RPAD, ptB, mB, l, alpha, S4s);
+        {
+            // the next task's residues: text and pattern of both pairs, eight 128-byte lines each
+            const PairMeta &M = (l & 16) ? nextB : nextA;
+            const uint8_t *base = (l & 8) ? A.pattern + M.p0 : A.text + M.t0;
+            const int len = (l & 8) ? M.m : M.n;
+            if ((l & 7) * 128 < len + 127) prefetch_l2(base + (l & 7) * 128);
         }
         __syncwarp();
 

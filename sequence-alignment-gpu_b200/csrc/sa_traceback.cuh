@@ -57,6 +57,11 @@ struct TbArgs {
     // column slice of a global alignment (sa_strip_traceback): the path starts at (start_row, n) on the right
     // edge; with `slice` set (not the first slice) it ends on the left edge instead of running up column 0
     int start_given, start_row, slice;
+    // row chunk of a checkpointed (linear-space) global traceback: the path enters on the chunk's bottom row at the
+    // column *start_col_dev (device value: it is where the chunk below was left) and, with chunk_top set, ends on the
+    // chunk's top row instead of running along the matrix border; the column where it leaves goes to *exit_col_dev and
+    // the piece is appended in front of what the chunks below have emitted (*global_off steps so far)
+    const int *start_col_dev;  int chunk_top;  unsigned long long *global_off;  int *exit_col_dev;
     // fill results
     const int *cand_v; const uint32_t *cand_i; const uint32_t *cand_j;
     int32_t *score;
@@ -144,7 +149,7 @@ __global__ void tb_prepare_kernel(const TbArgs A)
         *A.score = H0;
         A.res[3] = (uint64_t)i0 * (uint64_t)(n + 1) + (uint64_t)j0;
     } else if (A.start_given) {
-        H0 = 0; i0 = A.start_row; j0 = n;
+        H0 = 0; i0 = A.start_row; j0 = A.start_col_dev ? *A.start_col_dev : n;
         A.res[3] = 0;
     } else {
         H0 = *A.score; i0 = m; j0 = n;
@@ -248,6 +253,7 @@ __device__ __forceinline__ void tb_segment(const TbArgs &A, const int t)
     while (true) {
         if (A.local) { if (i <= stop_row || i == 0 || j == 0) break; }
         else if (A.slice) { if (j == 0 || (t > 0 && i <= stop_row)) break; }      // row 0 runs LEFT to the slice edge
+        else if (A.chunk_top) { if (i <= stop_row) break; }                        // row chunk: ends on its top row
         else if (t == 0) { if (i == 0 && j == 0) break; }
         else if (i <= stop_row) break;
         if (MODE == 1 && budget == 0) break;
@@ -306,7 +312,7 @@ __global__ void tb_offsets_kernel(const TbArgs A)
         A.res[0] = 0; A.res[1] = ~0ull; A.res[2] = ~0ull;
         return;
     }
-    unsigned long long off = 0;
+    unsigned long long off = A.global_off ? *A.global_off : 0ull;
     long long H = A.st->H0;
     int cut = -1;
     int ei = 0, ej = 0;                 // cell reached after the last emitted step
@@ -342,6 +348,8 @@ __global__ void tb_offsets_kernel(const TbArgs A)
     A.st->cut_seg = cut;
     A.st->total_len = off;
     A.res[0] = off;
+    if (A.global_off) *A.global_off = off;
+    if (A.exit_col_dev) *A.exit_col_dev = A.X[0];
     if (!A.local && A.start_given) { A.res[1] = (uint64_t)A.st->exit_row; A.res[2] = 0; A.res[3] = 0; return; }
     if (!A.local) { A.res[1] = 0; A.res[2] = 0; return; }      // clamped indices end at 0 (alignSequenceCPU.cpp:100-101)
     if (!haveExit) {

@@ -791,3 +791,68 @@ def test_device_side_identity_and_gap_counts(sa, aligner, oracle, force_path, mo
             for i in list(range(0, N, 97)) + [N - 1]:
                 a = sa.unpack_batch(out, i)
                 assert (int(out["stats"][2 * i]), int(out["stats"][2 * i + 1])) == counts(a), (N, mode, i)
+
+
+def test_config5_recipe_score_pinned_by_the_cpu_oracle(sa, aligner):
+    """BASELINE config 5's seeded pair (seeds 777 / 778) at 100 000 letters, as column slices: the score equals
+    the CPU oracle's (tests/golden/c5_golden.json, made by tests/golden/make_c5_golden.py; the same file pins the
+    1 000 000-letter score 3 972 370 that bench.py / bench_c5.py compare the multi-GPU run with)."""
+    import json
+    import synth
+    gold = json.load(open(os.path.join(helpers.GOLD, "c5_golden.json")))
+    assert gold["1000000"]["score"] == 3972370 and gold["1000000"]["m"] == 950793
+    t, p = synth.synthetic_pair(100000, 777, 778)
+    g = gold["100000"]
+    assert (len(t), len(p)) == (g["n"], g["m"])
+    blast = helpers.matrices()["dna/blast.txt"]
+    a = _strip_align(sa, 4, blast, 5, t, p, 3)
+    assert a.score == g["score"]
+    assert_same(a, aligner.align(0, 4, blast, 5, t, p), "slices vs single matrix")
+
+
+@pytest.mark.parametrize("variant", [dict(SA_CKPT_ROWS="300"), dict(SA_CKPT_ROWS="1000", SA_TILE="8,2"), dict(SA_CKPT_ROWS="700", SA_LONG_KERNEL="strip"),
+                                     dict(SA_CKPT_ROWS="129", SA_TB_WD="16"), dict(SA_CKPT_ROWS="2000", SA_TB_BAND="1")])
+def test_checkpointed_traceback_vs_oracle(aligner, oracle, force_path, monkeypatch, variant):
+    """Linear-space traceback: the matrix is filled in row chunks that keep only an H row each, then every
+    chunk is filled again from its checkpoint and walked, last chunk first.  Same Response as the single-matrix path and
+    the oracle, byte for byte, whatever the chunk height, kernel and candidate spacing; the device-side identity / gap
+    counts add up over the chunks.  (Local alignments never take this path.)"""
+    force_path("long")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(777)
+    blast = helpers.matrices()["dna/blast.txt"]
+    b62 = helpers.matrices()["protein/blosum62.txt"]
+    cases = []
+    for it in range(8):
+        alpha, mat = (4, blast) if it % 2 == 0 else (23, b62)
+        t, p = helpers.random_case(rng, alpha, n_max=[700, 2500, 6000][it % 3], similar=it % 4 != 3)
+        cases.append((alpha, mat, t, p))
+    cases.append((4, blast, rng.integers(0, 4, 3000, dtype=np.uint8), rng.integers(0, 4, 2500, dtype=np.uint8)))      # unrelated: the path meanders
+    cases.append((4, blast, np.zeros(2000, np.uint8), np.zeros(1700, np.uint8)))                                    # ties everywhere
+    cases.append((4, blast, rng.integers(0, 4, 900, dtype=np.uint8), rng.integers(0, 4, 2600, dtype=np.uint8)))       # more rows than columns
+    for alpha, mat, t, p in cases:
+        for gap in (2, 7):
+            want = oracle.align(0, alpha, mat, gap, t, p)
+            got = aligner.align(0, alpha, mat, gap, t, p)
+            assert_same(got, want, (variant, alpha, gap, len(t), len(p)))
+            st = aligner.last_stats()
+            ident = sum(1 for a, b in zip(want.aligned_text, want.aligned_pattern) if a == b)
+            gaps = sum(1 for a, b in zip(want.aligned_text, want.aligned_pattern) if a == ord("-") or b == ord("-"))
+            assert st == (ident, gaps), (variant, len(t), len(p))
+            # a local alignment of the same pair is untouched by the switch
+            assert_same(aligner.align(1, alpha, mat, gap, t, p), oracle.align(1, alpha, mat, gap, t, p), (variant, "local"))
+
+
+def test_checkpointed_traceback_full_size_c3(aligner, oracle, monkeypatch):
+    """Config 3 (100 000 x 95 217) through the checkpointed path in 5 row chunks: the reference's known answer."""
+    import synth
+    t, p = synth.synthetic_pair(100000, 12345, 54321)
+    blast = helpers.matrices()["dna/blast.txt"]
+    plain = aligner.align(0, 4, blast, 5, t, p)
+    launches = aligner.timing()["kernel_launches"]
+    monkeypatch.setenv("SA_CKPT_ROWS", "20000")
+    a = aligner.align(0, 4, blast, 5, t, p)
+    assert aligner.timing()["kernel_launches"] >= 5 * launches          # 5 fills + 4 re-fills + 5 tracebacks
+    assert (a.score, a.aln_len, a.start_text, a.start_pattern) == (399463, 100254, 0, 0)
+    assert_same(a, plain, "checkpointed vs single matrix")

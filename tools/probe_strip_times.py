@@ -19,6 +19,8 @@ m = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 t, p = synth.synthetic_pair(n, 12345, 54321)
 if m:
     p = p[:m]
+if os.environ.get("SLICE"):          # a column slice of the pair (config 5 shape: few columns, all rows)
+    t = t[:int(os.environ["SLICE"])]
 dbg = tempfile.mktemp(prefix="sa_dbg_")
 os.environ["SA_LONG_DBG"] = dbg
 mat = np.full((4, 4), -4, np.int32)

@@ -13,8 +13,9 @@ contiguous ranges (sa_partition_batch), rank r aligns range r, no data-path
 collective.  --scaling weak gives every rank its own --pairs pairs instead.
 c1/c2/c3 are the single-pair configs (replicas only at N>1).  After the main
 measurement the line also carries config 5 (`c5`: one long global alignment as
-column slices over the N GPUs; at N=1 the longest pair whose directions fit one
-GPU comfortably) unless --c5 off.
+column slices over the N GPUs; at N=1 the same 1 000 000 x 950 793 pair through the
+checkpointed linear-space traceback, its 250 GB of directions never held at once)
+unless --c5 off.
 
   value  = whole-job GCUPS with inputs resident in HBM (sa_align_batch_device /
            sa_align_device on torch's stream), fill + device traceback + string emission;
@@ -530,7 +531,7 @@ def run_ours(args, rank, world, local_rank):
         gc.collect()
         torch.cuda.empty_cache()
         from bench_c5 import run_c5
-        length = int(args.c5) if args.c5 != "auto" else (1_000_000 if world >= 2 else 500_000)
+        length = int(args.c5) if args.c5 != "auto" else 1_000_000
         try:
             c5 = run_c5(sa, rank, world, local_rank, length, steps=2)          # best of two: the first call pays the allocations
         except SystemExit as e:          # does not fit: say so instead of failing the headline line
@@ -559,7 +560,7 @@ def main():
                     help="c4 over N GPUs: strong = ONE batch of --pairs pairs sharded over the ranks (BASELINE config 4), "
                          "weak = --pairs pairs on every rank")
     ap.add_argument("--verify-pairs", type=int, default=16384, help="pairs of each output set checked against the reference after the timed regions")
-    ap.add_argument("--c5", default="auto", help="config 5 beside the main line: auto (1 000 000 at N >= 2, 500 000 at N = 1), off, or a length")
+    ap.add_argument("--c5", default="auto", help="config 5 beside the main line: auto (1 000 000: column slices at N >= 2, the checkpointed traceback at N = 1), off, or a length")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

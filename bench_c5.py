@@ -6,8 +6,8 @@
 
 Workload: base = `length` letters uniform over ATCG (random.seed(777)), partner = mutate.py-style
 copy (random.seed(778)); NW, blast.txt, gap 5.  Rank k owns columns [k*W, (k+1)*W) and that slice's packed
-direction words (length 1 000 000 -> 250 GB in total, so N >= 2).  At N = 1 the same code path runs on one GPU
-for lengths whose directions fit.  Prints one JSON line on rank 0: GCUPS including traceback (barrier to
+direction words (length 1 000 000 -> 250 GB in total).  At N = 1 the same code path runs on one GPU for lengths whose
+directions fit, and the full length goes through the library's checkpointed (linear-space) traceback.  Prints one JSON line on rank 0: GCUPS including traceback (barrier to
 barrier, max over ranks), per-rank fill times, and the checks that do not need the (infeasible, 1 TB)
 reference matrix: re-scoring the emitted alignment reproduces the score and the strings spell the inputs.
 """
@@ -55,11 +55,14 @@ def run_c5(sa, rank, world, local_rank, length, steps=1, linked=True, chunks=1, 
     blast = np.array([[5 if i == j else -4 for j in range(4)] for i in range(4)], np.int32)   # scoreMatrices/dna/blast.txt
     c0, w = strips.slice_columns(n, world)[rank]
     need = (w + 63) * (m + 511) / 4
-    free, _ = torch.cuda.mem_get_info()
-    if need > 0.95 * free:
+    free, total = torch.cuda.mem_get_info()
+    # one GPU and a direction matrix beyond its memory: the library's checkpointed (linear-space) traceback -- row chunks
+    # that keep one H row each, filled twice (sa_align -> enqueue_long_checkpointed)
+    checkpointed = world == 1 and need > 0.6 * total
+    if need > 0.95 * free and not checkpointed:
         raise SystemExit(f"rank {rank}: slice needs {need / 1e9:.1f} GB of direction words, {free / 1e9:.1f} GB free -- use more GPUs")
     al = sa.Aligner(local_rank)
-    eng = strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, n, p, device=f"cuda:{local_rank}")
+    eng = None if checkpointed else strips.GpuStripEngine(al, 4, blast, 5, t[c0:c0 + w], c0, n, p, device=f"cuda:{local_rank}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -71,7 +74,12 @@ def run_c5(sa, rank, world, local_rank, length, steps=1, linked=True, chunks=1, 
     for _ in range(steps):
         barrier()
         t0 = time.perf_counter()
-        if world > 1 and linked:
+        fill_ms = None
+        if checkpointed:
+            a = al.align(0, 4, blast, 5, t, p)
+            res = (a.score, a.aligned_text, a.aligned_pattern, a.start_text, a.start_pattern)
+            fill_ms = al.timing()["fill_us"] / 1e3
+        elif world > 1 and linked:
             res = strips.align_pair_strips_linked(eng, m, rank, world)
         elif world > 1:
             res = strips.align_pair_strips(eng, m, rank, world, eng.column_buffer, chunks=chunks)
@@ -79,7 +87,7 @@ def run_c5(sa, rank, world, local_rank, length, steps=1, linked=True, chunks=1, 
             res = strips.align_pair_strips_local([eng], m, chunks=chunks)
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, eng.fill_ms or 0.0], dtype=torch.float64, device=dev)
+        tt = torch.tensor([dt, (fill_ms if checkpointed else eng.fill_ms) or 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             allt = [torch.zeros_like(tt) for _ in range(world)]
             dist.all_gather(allt, tt)
@@ -111,10 +119,13 @@ def run_c5(sa, rank, world, local_rank, length, steps=1, linked=True, chunks=1, 
                                         for (_, w_), f in zip(strips.slice_columns(n, world), fills)],
                    score=score, aln_len=len(at), checks=checks, dtype="int32", data="synthetic",
                    config=dict(workload=f"c5: NW {n} x {m} DNA, blast, gap 5", slices=world, row_chunks=chunks,
-                               pipeline="linked in-launch hand-off over peer memory (strips of neighbouring GPUs overlap)" if linked and world > 1
+                               pipeline="one GPU, checkpointed linear-space traceback: row chunks keep one H row each and are filled twice "
+                                        "(host buffers, copies inside the timed region)" if checkpointed
+                               else "linked in-launch hand-off over peer memory (strips of neighbouring GPUs overlap)" if linked and world > 1
                                else "rank k fills row chunk c while rank k+1 fills chunk c-1" if chunks > 1
                                else "slices run one after the other"))
-    eng.linked_release(barrier if world > 1 else None)
+    if eng is not None:
+        eng.linked_release(barrier if world > 1 else None)
     del eng
     al.close()
     torch.cuda.empty_cache()

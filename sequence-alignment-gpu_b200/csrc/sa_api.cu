@@ -786,10 +786,11 @@ int tile_blocks_per_sm(const sa_context *ctx, uint64_t n, int C, int occ)
 }
 
 // Which long-pair kernel, measured on B200 (tools/probe_tile.py, profiles/README.md round 2).  The register-tiled kernel
-// (sa_tile.cuh) is built for the latency-bound regime -- at most a few strips per SM scheduler, i.e. up to ~300 k rows:
+// (sa_tile.cuh) is built for the latency-bound regime -- at most a few strips per SM scheduler:
 // 100 000 x 95 217 fills in 10.3 ms with 8 x 2 tiles against 13.7 ms (one-column kernel), 4 000 x 3 800 in 0.41 against
-// 0.61 ms.  With many strips per scheduler (a 125 000-column slice of config 5 has 3 716) the warps hide each other's
-// latencies and the one-column kernel with tall strips issues fewer instructions per cell: 59 ms against 75 ms.
+// 0.61 ms.  With its residency capped by tile_blocks_per_sm it also wins on the tall shapes: a 125 000-column slice of
+// config 5 (3 716 strips) in 51 ms against 59 ms (one-column kernel, strips of 512 rows), 1 000 000 x 390 000 (a chunk of
+// the checkpointed traceback) in 147 against 181 ms; 500 000 x 475 000 is a tie (112 / 114 ms).
 // SA_TILE="R,C" forces a tile shape; SA_LONG_R or SA_LONG_KERNEL=strip force the one-column kernel (always the path
 // of wide score matrices).
 bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int slices, int *R, int *C)
@@ -805,7 +806,7 @@ bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int slices, i
     // starts when strip 0 has crossed k slices, and a tiled strip crosses a 125 000-column slice in 8 ms against 17 ms.
     int r = 8, c = 2;
     if (traceback && m <= 16000) { r = 4; c = 4; }
-    bool use = (m <= 300000 || slices >= 4) && !local;
+    bool use = (m <= 480000 || slices >= 4) && !local;
     if (const char *e = std::getenv("SA_TILE")) {
         int er = 0, ec = 0;
         if (std::sscanf(e, "%d,%d", &er, &ec) == 2 && tile_cfg_exists(er, ec)) { r = er; c = ec; use = true; }
@@ -1136,7 +1137,7 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
 
 // When the packed directions of a GLOBAL alignment would not fit the device (or SA_CKPT_ROWS forces it), the pair takes the
 // checkpointed path.  SA_CKPT_LIMIT_MB: direction bytes above which it is taken (default 60 % of the device memory);
-// SA_CKPT_CHUNK_MB: direction bytes of one row chunk (default 16 GB: 65 536 rows of a 1 000 000-column matrix).
+// SA_CKPT_CHUNK_MB: direction bytes of one row chunk (default: half the device memory).
 bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, bool traceback, uint64_t *chunk_rows)
 {
     if (!traceback || sc->mode != SA_GLOBAL || ctx->wide) return false;
@@ -1151,12 +1152,14 @@ bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_
     long double limit = 0.6L * (long double)totalB;
     if (const char *e = std::getenv("SA_CKPT_LIMIT_MB")) limit = (long double)std::atoll(e) * 1048576.0L;
     if (dirBytes <= limit) return false;
-    long double chunkBytes = 16.0L * 1073741824.0L;
+    // chunks as tall as the memory allows, all of the same height: a chunk is one launch of the long-pair kernel, and a
+    // wide, low matrix keeps few strips busy (1 000 000 columns: 65 536 rows fill at 0.9 TCUPS, 390 000 rows at 2.7)
+    long double chunkBytes = std::min(limit, 0.5L * (long double)totalB);
     if (const char *e = std::getenv("SA_CKPT_CHUNK_MB")) chunkBytes = (long double)std::atoll(e) * 1048576.0L;
-    chunkBytes = std::min(chunkBytes, limit);
-    const uint64_t rows = (uint64_t)(chunkBytes * 4.0L / (long double)(n + 64));
-    *chunk_rows = std::max<uint64_t>(1024, rows);
-    return *chunk_rows < m;
+    const uint64_t rowsMax = std::max<uint64_t>(1024, (uint64_t)(chunkBytes * 4.0L / (long double)(n + 64)));
+    const uint64_t K = (m + rowsMax - 1) / rowsMax;
+    *chunk_rows = (m + K - 1) / K;
+    return K > 1;
 }
 
 // enqueue_long, or its checkpointed form when the direction matrix is too large for the device

@@ -770,17 +770,20 @@ struct LongPlan {
     size_t strip_stride, row_stride, smem;
 };
 
-// Resident blocks per SM of a tiled fill.  The strips form a chain in which strip s+1 runs one hand-off lag (~55 macro-steps,
-// see DESIGN.md 4.2) behind strip s, so only (macro-steps of a sweep) / 55 strips can be busy at a time; warps beyond that
-// only slow the busy ones down -- the lag, which every one of the n_strips pays, is a number of macro-steps.  Measured on a
-// 125 000-column slice of config 5 (3716 strips): 76.8 / 57.0 / 63.5 / 72.6 ms with 1 / 2 / 3 / 4 blocks per SM, and strip 0
-// crosses the slice in 9.5 / 11.8 / 13.7 / 14.8 ms (the delay per GPU of the linked slices).  SA_LONG_BLOCKS_PER_SM overrides.
-int tile_blocks_per_sm(const sa_context *ctx, uint64_t n, int C, int occ)
+// Resident blocks per SM of a tiled fill: two (two warps per SM scheduler).  One tiled warp keeps its scheduler about
+// half busy, so two saturate it; warps beyond that only stretch every macro-step -- and with it the hand-off lag that each
+// of the n_strips strips pays (~55 macro-steps) and the time strip 0 needs to cross a column slice, which is
+// the delay per GPU of the linked slices of config 5.  Measured: a 125 000-column slice (3 716 strips) fills in 76.8 / 57.0 /
+// 63.5 / 72.6 ms with 1 / 2 / 3 / 4 blocks per SM and strip 0 crosses it in 9.5 / 11.8 / 13.7 / 14.8 ms; a 250 000-column
+// slice in 105 / 102 / 105 ms with 2 / 3 / 4, and config 5 on 4 GPUs in 0.199 / 0.218 / 0.236 s.  SA_LONG_BLOCKS_PER_SM overrides.
+// A fill whose strips all fit with three blocks per SM but not with two takes three (a second wave of a few strips costs a
+// whole sweep: 1 000 000 x 317 000, a chunk of the checkpointed traceback, 192 ms with two and 137 ms with three).
+int tile_blocks_per_sm(const sa_context *ctx, uint64_t n_strips, int slices, int occ)
 {
-    int perSm = std::min(occ, 8);
-    const uint64_t busy = (n / (uint64_t)C + 31) / 55 + 1;
     const uint64_t perBlockSm = (uint64_t)ctx->sms * TILE_WARPS;
-    perSm = (int)std::min<uint64_t>((uint64_t)perSm, std::max<uint64_t>(1, (busy + perBlockSm - 1) / perBlockSm));
+    int perSm = 2;
+    if (slices <= 1 && n_strips > 2 * perBlockSm && n_strips <= 3 * perBlockSm) perSm = 3;
+    perSm = std::min(occ, perSm);
     if (const char *e = std::getenv("SA_LONG_BLOCKS_PER_SM")) { const int b = std::atoi(e); if (b >= 1) perSm = std::min(occ, b); }
     return perSm;
 }
@@ -802,11 +805,12 @@ bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int slices, i
     // passes of the parallel traceback short (3 903 x 3 698: fill + traceback 0.82 ms against 0.99).  Local alignments stay
     // on the one-column kernel: the per-tile arg-max test costs the tiled sweep its advantage (100 k x 95 k SW: 29.6 ms
     // tiled, 27.8 ms one-column; both ~2.8x the global fill -- the next thing to fix on this path).
-    // A column slice of a pair that is spread over 4 or more GPUs is latency-bound again, whatever its height: GPU k
-    // starts when strip 0 has crossed k slices, and a tiled strip crosses a 125 000-column slice in 8 ms against 17 ms.
+    // Column slices (config 5): GPU k starts when strip 0 has crossed k slices, and a tiled strip crosses a 125 000-column
+    // slice in 12 ms against 22 ms; 1 000 000 x 950 793 on 2 GPUs takes 0.274 s tiled, 0.328 s with the one-column kernel.
+    (void)slices;
     int r = 8, c = 2;
     if (traceback && m <= 16000) { r = 4; c = 4; }
-    bool use = (m <= 480000 || slices >= 4) && !local;
+    bool use = !local;
     if (const char *e = std::getenv("SA_TILE")) {
         int er = 0, ec = 0;
         if (std::sscanf(e, "%d,%d", &er, &ec) == 2 && tile_cfg_exists(er, ec)) { r = er; c = ec; use = true; }
@@ -857,7 +861,7 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
         const int occ = tile_occupancy(tR, tC, local, linked, P->smem);
         if (occ < 1) return SA_ERR_LAUNCH;
         // every strip of a launch should be resident at once when it can be: up to 8 blocks (32 strips) per SM
-        const int perSm = tile_blocks_per_sm(ctx, n, tC, occ);
+        const int perSm = tile_blocks_per_sm(ctx, P->n_strips, slices, occ);
         const uint64_t maxBlocks = (uint64_t)ctx->sms * perSm;
         const uint64_t needBlocks = (P->n_strips + TILE_WARPS - 1) / TILE_WARPS;
         P->grid = (int)std::min(maxBlocks, needBlocks);
@@ -1638,7 +1642,7 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     int occ = S.C ? tile_occupancy(S.R, S.C, false, linkedKernel, S.smem) : occupancy_long(S.R, false, S.smem, linkedKernel);
     if (occ < 1) return SA_ERR_LAUNCH;
     int perSm = std::min(occ, 2);
-    if (S.C) perSm = tile_blocks_per_sm(ctx, S.n, S.C, occ);
+    if (S.C) perSm = tile_blocks_per_sm(ctx, nStrips, (int)std::min<uint64_t>(64, (S.total + S.n / 2) / S.n), occ);
     else if (const char *e = std::getenv("SA_LONG_BLOCKS_PER_SM")) { const int b = std::atoi(e); if (b >= 1) perSm = std::min(occ, b); }
     const uint64_t maxBlocks = (uint64_t)ctx->sms * perSm;
     const int grid = (int)std::min<uint64_t>(maxBlocks, (nStrips + LONG_WARPS - 1) / LONG_WARPS);

@@ -17,13 +17,15 @@ constexpr int NCHAIN = 8;
 constexpr int ITERS = 4096;
 
 enum Op { IADD, LOP3, SHFT, IMAD, IMADSHL, DP4A, VMAX, VMAX3, VADDMAX, VADDMAXRELU, SETPSEL, PRMTOP,
-          PREDOR, VADDMAX16, VADDMAX16RELU, VMAX316, VADD16, VBMAX16, CELL16, MIX_VADDMAX_IMAD, MIX_VADDMAX_DP4A, MIX_LOP_IMAD, MIX_VMAX3_DP4A_IMAD, CELL_TAG, CELL_PRED, NOPS };
+          PREDOR, VADDMAX16, VADDMAX16RELU, VMAX316, VADD16, VBMAX16, CELL16, CELL16B, CELL16N, MIX_VADDMAX_IMAD, MIX_VADDMAX_DP4A, MIX_LOP_IMAD, MIX_VMAX3_DP4A_IMAD, CELL_TAG, CELL_PRED, NOPS };
 static const char* opname[NOPS] = {"IADD3", "LOP3", "SHF", "IMAD", "IMAD.SHL", "IDP.4A", "VIMNMX", "VIMNMX3", "VIADDMNMX",
     "VIADDMNMX.RELU", "ISETP+SEL", "PRMT", "ISETP+@P LOP3", "VIADDMNMX.S16x2", "VIADDMNMX.S16x2.RELU", "VIMNMX3.S16x2",
-    "VIADD.16x2 (__vadd2)", "VIMNMX.S16x2+preds (__vibmax_s16x2)", "cell16(PRMT,VIADD.16x2,2xVIADDMNMX.S16x2,LOP3,2xIMAD; 2 cells)", "VIADDMNMX+IMAD", "VIADDMNMX+IDP.4A", "LOP3+IMAD",
+    "VIADD.16x2 (__vadd2)", "VIMNMX.S16x2+preds (__vibmax_s16x2)", "cell16(PRMT,VIADD.16x2,2xVIADDMNMX.S16x2,LOP3,2xIMAD; 2 cells)",
+    "cell16b(PRMT,VIADDMNMX.S16x2,VIMNMX3.S16x2,LOP3,4xIMAD: both adds as 32-bit IMAD on a biased low half; 2 cells)",
+    "cell16n(PRMT,2xVIADDMNMX.S16x2,LOP3,2xIMAD: left candidate carried un-added; 2 cells)", "VIADDMNMX+IMAD", "VIADDMNMX+IDP.4A", "LOP3+IMAD",
     "VIMNMX3+IDP+IMAD", "cell(tagged:LOP3,2xVIADDMNMX,IDP,2xIMAD)", "cell(pred:2xVIMNMX,IADD,IDP,2xISETP,2x@P LOP3)"};
 // lane-ops counted per inner iteration per chain
-static const int opcount[NOPS] = {1,1,1,1,1,1,1,1,1,1,2,1,2,1,1,1,1,1,7,2,2,2,3,6,8};
+static const int opcount[NOPS] = {1,1,1,1,1,1,1,1,1,1,2,1,2,1,1,1,1,1,7,8,6,2,2,2,3,6,8};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(int* out, int a0, int b0, int c0)
@@ -57,10 +59,34 @@ __global__ void __launch_bounds__(1024) k(int* out, int a0, int b0, int c0)
             if (OP == CELL16) {
                 // the packed batch cell (sa_batch16.cuh): two cells (one per 16-bit half) per pass
                 unsigned s2, cl, m, h, cn;
-                asm volatile("prmt.b32 %0, %1, %2, 0x9180;" : "=r"(s2) : "r"(b), "r"(c));
+                asm volatile("prmt.b32 %0, %1, %2, 0x9180;" : "=r"(s2) : "r"(w[(i + 1) % NCHAIN]), "r"(c));      // (an operand that changes: ptxas hoists a loop-invariant PRMT)
                 cl = __vadd2((unsigned)v[i], (unsigned)b);
                 m = __viaddmax_s16x2((unsigned)w[i], s2, cl);
                 h = __viaddmax_s16x2_relu((unsigned)v[i], (unsigned)c, m);
+                cn = h & 0xFFFCFFFCu;
+                asm volatile("mad.lo.s32 %0, %1, 16, %0;" : "+r"(w[i]) : "r"(h));
+                asm volatile("mad.lo.s32 %0, %1, -16, %0;" : "+r"(w[i]) : "r"(cn));
+                v[i] = (int)cn;
+            }
+            if (OP == CELL16B) {
+                // the same cell with both constant adds on the FMA pipe (32-bit IMAD; the low half is biased so that it never
+                // changes sign and the carry into the high half is a constant) and the zero clamp as a third max operand
+                unsigned s2, cl, ct, m, h, cn;
+                asm volatile("prmt.b32 %0, %1, %2, 0x9180;" : "=r"(s2) : "r"(w[(i + 1) % NCHAIN]), "r"(c));      // (an operand that changes: ptxas hoists a loop-invariant PRMT)
+                asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(cl) : "r"(v[i]), "r"(a0), "r"(b));
+                m = __viaddmax_s16x2((unsigned)w[i], s2, cl);
+                asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(ct) : "r"(v[i]), "r"(a0), "r"(c));
+                h = __vimax3_s16x2(ct, m, (unsigned)b);
+                cn = h & 0xFFFCFFFCu;
+                asm volatile("mad.lo.s32 %0, %1, 16, %0;" : "+r"(w[i]) : "r"(h));
+                asm volatile("mad.lo.s32 %0, %1, -16, %0;" : "+r"(w[i]) : "r"(cn));
+                v[i] = (int)cn;
+            }
+            if (OP == CELL16N) {
+                unsigned s2, m, h, cn;
+                asm volatile("prmt.b32 %0, %1, %2, 0x9180;" : "=r"(s2) : "r"(w[(i + 1) % NCHAIN]), "r"(c));      // (an operand that changes: ptxas hoists a loop-invariant PRMT)
+                m = __viaddmax_s16x2((unsigned)w[i], s2, (unsigned)v[i]);
+                h = __viaddmax_s16x2((unsigned)v[i], (unsigned)c, m);
                 cn = h & 0xFFFCFFFCu;
                 asm volatile("mad.lo.s32 %0, %1, 16, %0;" : "+r"(w[i]) : "r"(h));
                 asm volatile("mad.lo.s32 %0, %1, -16, %0;" : "+r"(w[i]) : "r"(cn));
@@ -144,7 +170,7 @@ int main()
     run<IMADSHL>(d_out, sms, clk); run<DP4A>(d_out, sms, clk); run<VMAX>(d_out, sms, clk); run<VMAX3>(d_out, sms, clk);
     run<VADDMAX>(d_out, sms, clk); run<VADDMAXRELU>(d_out, sms, clk); run<SETPSEL>(d_out, sms, clk); run<PRMTOP>(d_out, sms, clk);
     run<PREDOR>(d_out, sms, clk); run<VADDMAX16>(d_out, sms, clk); run<VADDMAX16RELU>(d_out, sms, clk); run<VMAX316>(d_out, sms, clk);
-    run<VADD16>(d_out, sms, clk); run<VBMAX16>(d_out, sms, clk); run<CELL16>(d_out, sms, clk); run<MIX_VADDMAX_IMAD>(d_out, sms, clk); run<MIX_VADDMAX_DP4A>(d_out, sms, clk);
+    run<VADD16>(d_out, sms, clk); run<VBMAX16>(d_out, sms, clk); run<CELL16>(d_out, sms, clk); run<CELL16B>(d_out, sms, clk); run<CELL16N>(d_out, sms, clk); run<MIX_VADDMAX_IMAD>(d_out, sms, clk); run<MIX_VADDMAX_DP4A>(d_out, sms, clk);
     run<MIX_LOP_IMAD>(d_out, sms, clk); run<MIX_VMAX3_DP4A_IMAD>(d_out, sms, clk); run<CELL_TAG>(d_out, sms, clk); run<CELL_PRED>(d_out, sms, clk);
     return 0;
 }

@@ -42,11 +42,27 @@ constexpr int TG = SA_TILE_TG;     // macro-steps per top-row group (prefetch di
 #endif
 constexpr int TG_REQ = SA_TILE_TG_REQ;   // macro-step of a group after which the next group is requested
 constexpr int TEXT_RING = 128;     // tiles of text kept in shared memory per warp
+// In-block hand-off (compile-time option, OFF): the strips of one block are neighbours in the chain, so lane 31 can store
+// the {4H, tag} words into a ring of HRING tiles in the NEXT warp's shared memory and that warp's top-row upkeep can poll
+// the ring instead of L2.  Built, bit-exact (the GPU parity tests pass with it) and measured slower on B200: config 3 fills
+// in 11.6 ms against 10.2 ms, a lone strip sweeps 9 % slower (the extra predicated store and the two-source upkeep change
+// the schedule of the straight-line macro-step) and the lag per strip does not shrink (11.8 us against 10.5 us in the
+// instrumented build): the lag is not the L2 round trip -- see DESIGN.md 4.2.  -DSA_TILE_HANDOFF=1 turns it on.
+#ifndef SA_TILE_HANDOFF
+#define SA_TILE_HANDOFF 0
+#endif
+#ifndef SA_TILE_RING_SLEEP
+#define SA_TILE_RING_SLEEP 40
+#endif
+constexpr int HRING_SHIFT = 8;
+constexpr int HRING = 1 << HRING_SHIFT;   // tiles of the in-block hand-off ring (the producer runs 9..60 tiles ahead)
 
 __host__ __device__ constexpr size_t tile_warp_smem(int R, int C, int alpha)
 {
-    // profile, text ring, top-row window (2*TG tiles), exchange buffer (C/2 parts of 32 x 2 ints)
-    return ((size_t)alpha * 32 * rpad_for(R) + (size_t)TEXT_RING * C + (size_t)2 * TG * C * 4 + (size_t)(C / 2) * 256 + 15) & ~(size_t)15;
+    // profile, text ring, top-row window (2*TG tiles), exchange buffer (C/2 parts of 32 x 2 ints), hand-off ring of
+    // HRING tiles x C {4H, tag} words + the consumer's progress word
+    return ((size_t)alpha * 32 * rpad_for(R) + (size_t)TEXT_RING * C + (size_t)2 * TG * C * 4 + (size_t)(C / 2) * 256 +
+            (SA_TILE_HANDOFF ? (size_t)HRING * C * 8 + 16 : 0) + 15) & ~(size_t)15;
 }
 
 __device__ __forceinline__ void ld_volatile_v2u64(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
@@ -67,6 +83,30 @@ __device__ __forceinline__ void st_row_words_if(const uint32_t flag, unsigned lo
                          "@q st.volatile.global.v4.u32 [%1+16], {%4, %6, %5, %6};\n\t}"
                          ::"r"(flag), "l"(p + cc), "r"(v[cc]), "r"(v[(cc + 1) % C]), "r"(v[(cc + 2) % C]), "r"(v[(cc + 3) % C]), "r"(tagHi) : "memory");
     }
+}
+
+// the same words into the hand-off ring of the next warp (shared memory), under one predicate
+template <int C>
+__device__ __forceinline__ void st_ring_words_if(const uint32_t flag, const uint32_t saddr, const int (&v)[C], const uint32_t tag)
+{
+#pragma unroll
+    for (int cc = 0; cc < C; cc += 2)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.volatile.shared.v4.u32 [%1], {%2, %4, %3, %4};\n\t}"
+                     ::"r"(flag), "r"(saddr + cc * 8), "r"(v[cc]), "r"(v[(cc + 1) % C]), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void lds_volatile_v2u64(const uint32_t saddr, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_volatile_u64(const uint32_t saddr)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_u64(const uint32_t saddr, const unsigned long long v)
+{
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
 }
 
 // Slow path of the SW arg-max: recompute one tile (plain cells, no tags) and return r*C + cc of the row-major first
@@ -116,6 +156,16 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
     unsigned char *textRing = profS + alpha * PS;
     int *topWin = reinterpret_cast<int *>(textRing + TEXT_RING * C);
     int *xbuf = topWin + 2 * TG * C;
+    // in-block hand-off: this warp's ring (filled by the warp above) and progress word (read by the warp above)
+    const uint32_t sRing = (uint32_t)__cvta_generic_to_shared(xbuf + (C / 2) * 64);
+    const uint32_t sProg = sRing + HRING * C * 8;
+    const uint32_t sRingDown = sRing + (uint32_t)tile_warp_smem(R, C, alpha), sProgDown = sProg + (uint32_t)tile_warp_smem(R, C, alpha);
+    if (SA_TILE_HANDOFF) {
+        // ring words of an earlier launch must never match: the ring starts out zeroed and every tag has bit 31 set
+        for (int i = lane; i < HRING * C / 2; i += 32)
+            asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sRing + i * 16), "r"(0u) : "memory");
+        if (lane == 0) sts_volatile_u64(sProg, ~0ull);
+    }
     for (int i = threadIdx.x; i < 32 * MAX_ALPHA; i += blockDim.x) S4s[i] = A.S4[i];
     __syncthreads();
     const unsigned char *profL = profS + lane * RPAD;       // this lane's R profile bytes of letter 0
@@ -127,8 +177,14 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
     const int nFull = n / C;                     // tiles that lie completely inside the text
     const int kEnd = nTiles + 31;                // macro-steps of a strip
 
-    for (uint32_t s = blockIdx.x * WARPS + warp; s < A.n_strips; s += W) {
+    uint32_t wave = 0;
+    for (uint32_t s = blockIdx.x * WARPS + warp; s < A.n_strips; s += W, ++wave) {
         const int row0 = (int)s * ROWS;                 // pattern index of the strip's first row
+        // the strip above / below belongs to the neighbouring warp of this block (same wave): hand-off in shared memory
+        const bool upInBlock = SA_TILE_HANDOFF == 1 && warp > 0 && s > 0;          // (2: dev aid, the ring is written but not read)
+        const bool downInBlock = SA_TILE_HANDOFF && warp + 1 < WARPS && s + 1 < A.n_strips;
+        // this warp is done with its previous strip: the warp above may overwrite the ring (progress = {wave, tiles copied})
+        if (SA_TILE_HANDOFF && lane == 0) sts_volatile_u64(sProg, (unsigned long long)wave << 32);
         // ---- query profile of this strip: prof[a][lane*RPAD + r] = 4*S[p_row][a], padding rows -128 ----
         __syncwarp();
         for (int i = lane; i < ROWS; i += 32) {
@@ -209,8 +265,11 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         const bool hasUp = s > 0, hasDown = s + 1 < A.n_strips;
         // lane 31 publishes the strip's bottom row for the strip below -- or, for the last strip of a row chunk, for
         // long_bottom_row_kernel, which copies it out of the ring
-        const bool writesRow = lane == 31 && (hasDown || A.bottom_row != nullptr);
+        const bool writesRow = lane == 31 && ((hasDown && !(downInBlock && SA_TILE_HANDOFF == 1)) || (!hasDown && A.bottom_row != nullptr));
         const uint32_t writesFlag = writesRow ? 1u : 0u;
+        const uint32_t ringFlag = (lane == 31 && downInBlock) ? 1u : 0u;
+        // ring words carry {wave, tile / HRING}: a slot read before its tile has arrived never matches
+        const uint32_t ringTagBase = 0x80000000u | ((wave & 0x7fu) << 24);
         const unsigned long long *rowIn = A.rowbuf + (size_t)((s + A.ring - 1) % A.ring) * A.row_stride;
         unsigned long long *rowOut = A.rowbuf + (size_t)(s % A.ring) * A.row_stride;
         const uint32_t wantTag = A.tag_base | s;          // producer s-1 writes (s-1)+1
@@ -225,30 +284,41 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         unsigned long long dbgSpins = 0, dbgSpinNs = 0, dbgStalls = 0, dbgRampStalls = 0, dbgEnter = 0, dbgExit = 0, dbgWrite = 0;      // (LINKED + dbg only)
         // group with first tile `first`: lanes q < TG own tile first + q (window slot (first + q) % (2*TG))
         auto request_top = [&](const int first) {
+            if (upInBlock) return;                       // shared memory: read when needed
             const int col = (first + lane) * C;
             if (lane < TG && col >= 0 && col < n) {
 #pragma unroll
                 for (int cc = 0; cc < C; cc += 2) ld_volatile_v2u64(rowIn + col + cc, pend[cc], pend[cc + 1]);
             }
         };
+        auto ring_load = [&](const int tile) {
+            const uint32_t a = sRing + (uint32_t)(tile & (HRING - 1)) * (C * 8);
+#pragma unroll
+            for (int cc = 0; cc < C; cc += 2) lds_volatile_v2u64(a + cc * 8, pend[cc], pend[cc + 1]);
+        };
         auto top_upkeep = [&](const int first) {
             const int col = (first + lane) * C;
             int tv[C];
             if (hasUp) {
                 const bool mine = lane < TG && col >= 0 && col < n;
+                const uint32_t want = upInBlock ? (ringTagBase | (((uint32_t)(first + lane) >> HRING_SHIFT) & 0xffffffu)) : wantTag;
+                if (upInBlock && mine) ring_load(first + lane);
                 const unsigned long long tSpin = (LINKED && A.dbg) ? gtime() : 0ull;
                 bool spun = false;
                 if (LINKED && A.dbg && first == 8001) dbgEnter = tSpin;
                 while (true) {
                     bool ok = true;
 #pragma unroll
-                    for (int cc = 0; cc < C; ++cc) ok = ok && (!(mine && col + cc < n) || (uint32_t)(pend[cc] >> 32) == wantTag);
+                    for (int cc = 0; cc < C; ++cc) ok = ok && (!(mine && col + cc < n) || (uint32_t)(pend[cc] >> 32) == want);
                     if (__all_sync(0xffffffffu, ok)) break;
                     if (LINKED && A.dbg) { spun = true; ++dbgSpins; }
                     if (!ok) {
-                        if (SA_TILE_SLEEP > 0) __nanosleep(SA_TILE_SLEEP);
+                        if (upInBlock) { if (SA_TILE_RING_SLEEP > 0) __nanosleep(SA_TILE_RING_SLEEP); ring_load(first + lane); }
+                        else {
+                            if (SA_TILE_SLEEP > 0) __nanosleep(SA_TILE_SLEEP);
 #pragma unroll
-                        for (int cc = 0; cc < C; cc += 2) ld_volatile_v2u64(rowIn + col + cc, pend[cc], pend[cc + 1]);
+                            for (int cc = 0; cc < C; cc += 2) ld_volatile_v2u64(rowIn + col + cc, pend[cc], pend[cc + 1]);
+                        }
                     }
                 }
                 if (LINKED && A.dbg && spun) { dbgSpinNs += gtime() - tSpin; ++dbgStalls; if (first <= 33) ++dbgRampStalls; }
@@ -265,10 +335,25 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                 for (int cc = 0; cc < C; ++cc) topWin[((first + lane) & (2 * TG - 1)) * C + cc] = tv[cc];
             }
             __syncwarp();
+            // the tiles below first + TG are out of the ring: tell the warp above
+            if (upInBlock && lane == 0) sts_volatile_u64(sProg, ((unsigned long long)wave << 32) | (uint32_t)max(0, first + TG));
             // The next group is NOT requested here but in the middle of this one (TG_REQ macro-steps later): requested
             // right away, the words of a producer that is only ~40 tiles ahead are not written yet, the reload at the
             // next group boundary costs an L2 round trip, and the lag a strip picks up that way while it starts stays
             // with it for the whole sweep (both run at the same speed) -- times the number of strips in the chain.
+        };
+        // Producer side of the in-block hand-off, once per group of macro-steps k .. k+TG-1: lane 31 is about to store the
+        // tiles up to k+TG-32 into the ring of the warp below.  That warp must have started this wave's strip (it is done
+        // with the previous one) and have copied the tiles that still occupy those slots.  (It runs ~41 tiles behind the
+        // stores, the ring holds 256: the wait only bites when the warp below is held up, e.g. by its left neighbour GPU.)
+        auto ring_space = [&](const int k) {
+            const int last = k + TG - 32;                // last tile stored during this group
+            if (!downInBlock || last < 0 || SA_TILE_HANDOFF != 1) return;
+            while (true) {               // (warp-uniform exit: lanes that leave a spin loop at different times stay split)
+                const unsigned long long pr = lds_volatile_u64(sProgDown);
+                if (__all_sync(0xffffffffu, (uint32_t)(pr >> 32) == wave && (int)(uint32_t)pr + HRING > last)) break;
+                __nanosleep(100);
+            }
         };
         // text ring upkeep, every 32 macro-steps: tiles k+32..k+63 become readable, k+64..k+95 are requested
         auto text_upkeep = [&](const int k) {
@@ -488,10 +573,19 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
             if (MODE != 0) {
                 const uint32_t wr = MODE == 1 ? writesFlag : MODE == 2 ? (kb >= 0 ? writesFlag : 0u) : (kb < nTiles ? writesFlag : 0u);
                 st_row_words_if<C>(wr, rowW, bot, (uint32_t)(myTagHi >> 32));
+                if (SA_TILE_HANDOFF) {
+                    const uint32_t wq = MODE == 1 ? ringFlag : MODE == 2 ? (kb >= 0 ? ringFlag : 0u) : (kb < nTiles ? ringFlag : 0u);
+                    st_ring_words_if<C>(wq, sRingDown + (uint32_t)(kb & (HRING - 1)) * (C * 8), bot, ringTagBase | (((uint32_t)kb >> HRING_SHIFT) & 0xffffffu));
+                }
             } else if (active && writesRow) {
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc)
                     if (cc < ncols) st_volatile_u64(rowW + cc, myTagHi | (uint32_t)bot[cc]);
+            } else if (SA_TILE_HANDOFF && active && ringFlag) {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc)
+                    if (cc < ncols) sts_volatile_u64(sRingDown + (uint32_t)(kb & (HRING - 1)) * (C * 8) + cc * 8,
+                                                     ((unsigned long long)(ringTagBase | (((uint32_t)kb >> HRING_SHIFT) & 0xffffffu)) << 32) | (uint32_t)bot[cc]);
             }
             rowW += C;
             if (LINKED && MODE == 1 && A.dbg && kb == 8008 && lane == 31) dbgWrite = gtime();
@@ -519,6 +613,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         if (LINKED && A.dbg && lane == 0) A.dbg[3 * A.n_strips + 4 * s] = gtime();
         for (int k = 0; k < kEnd; k += TG) {
             top_upkeep(k + 1);
+            if (SA_TILE_HANDOFF) ring_space(k);
             if (k >= 32 && (k & 31) == 0) text_upkeep(k);
             if (LINKED && A.dbg && lane == 0) {
                 if (k == 32) A.dbg[3 * A.n_strips + 4 * s + 1] = gtime();

@@ -483,7 +483,7 @@ def run_ours(args, rank, world, local_rank):
             if traffic is not None and w["kind"] == "batch":
                 traffic = traffic * (len(w["toff"]) - 1) / 1_000_000          # the capture is per 1 M pairs
             kname = ("batch_line16_kernel (all class launches of the step)" if w["kind"] == "batch"
-                     else "tile_fill_kernel" if w["mode"] == 0 and len(w["pattern"]) <= 300000 else "long_fill_kernel")
+                     else "tile_fill_kernel")
             line = dict(
                 metric="GCUPS incl. traceback", value=value, unit="GCUPS", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=total_ms_max / args.steps, higher_is_better=True,

@@ -102,6 +102,7 @@ struct sa_context {
     Slot slot[NIO_MAX];
     uint32_t epoch = 0;
     bool wide = false;                      // the scoring uploaded last needs the two-plane profile
+    int max_abs_score = 0;                  // ... and its largest |S|
     // sub-contexts for the long members of a host batch: several medium-size pairs run side by side (each is a
     // small cooperative launch), one host thread per sub-context
     std::vector<sa_context *> workers;
@@ -202,6 +203,8 @@ int upload_scoring(sa_context *ctx, const sa_scoring *sc, cudaStream_t st)
             hs[p * a + t] = v;
         }
     ctx->wide = wide;
+    ctx->max_abs_score = 0;
+    for (int i = 0; i < a * a; ++i) ctx->max_abs_score = std::max(ctx->max_abs_score, std::abs((int)sc->score_matrix[i]));
     SA_TRY(ctx->dS4.reserve(sizeof h4), SA_ERR_MEMORY);
     SA_TRY(ctx->dS.reserve(sizeof hs), SA_ERR_MEMORY);
     SA_TRY(cudaMemcpyAsync(ctx->dS4.p, h4, sizeof h4, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
@@ -796,24 +799,27 @@ int tile_blocks_per_sm(const sa_context *ctx, uint64_t n_strips, int slices, int
 // the checkpointed traceback) in 147 against 181 ms; 500 000 x 475 000 is a tie (112 / 114 ms).
 // SA_TILE="R,C" forces a tile shape; SA_LONG_R or SA_LONG_KERNEL=strip force the one-column kernel (always the path
 // of wide score matrices).
-bool pick_tile(uint64_t n, uint64_t m, bool traceback, bool local, int slices, int *R, int *C)
+bool pick_tile(const sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, bool traceback, bool local, int slices, int *R, int *C)
 {
-    (void)n;
     if (std::getenv("SA_LONG_R")) return false;
     if (const char *e = std::getenv("SA_LONG_KERNEL")) if (!std::strcmp(e, "strip")) return false;
     // 8 x 2 tiles fill fastest; when a traceback follows a small matrix, 4 x 4 (strips of 128 rows) keeps the per-strip
-    // passes of the parallel traceback short (3 903 x 3 698: fill + traceback 0.82 ms against 0.99).  Local alignments stay
-    // on the one-column kernel: the per-tile arg-max test costs the tiled sweep its advantage (100 k x 95 k SW: 29.6 ms
-    // tiled, 27.8 ms one-column; both ~2.8x the global fill -- the next thing to fix on this path).
+    // passes of the parallel traceback short (3 903 x 3 698: fill + traceback 0.82 ms against 0.99).  Local alignments
+    // take the same kernels with the branch-free arg-max key of sa_tile.cuh, as long as tile_scale(R) * S fits the
+    // one-byte profile and tile_scale(R) * H fits 32 bits; otherwise the one-column kernel.
     // Column slices (config 5): GPU k starts when strip 0 has crossed k slices, and a tiled strip crosses a 125 000-column
     // slice in 12 ms against 22 ms; 1 000 000 x 950 793 on 2 GPUs takes 0.274 s tiled, 0.328 s with the one-column kernel.
     (void)slices;
     int r = 8, c = 2;
     if (traceback && m <= 16000) { r = 4; c = 4; }
-    bool use = !local;
+    bool use = true;
     if (const char *e = std::getenv("SA_TILE")) {
         int er = 0, ec = 0;
-        if (std::sscanf(e, "%d,%d", &er, &ec) == 2 && tile_cfg_exists(er, ec)) { r = er; c = ec; use = true; }
+        if (std::sscanf(e, "%d,%d", &er, &ec) == 2 && tile_cfg_exists(er, ec)) { r = er; c = ec; }
+    }
+    if (local) {
+        const long double scale = tile_scale(r, true), big = std::max<long double>(sc->gap, ctx->max_abs_score);
+        if (ctx->max_abs_score * (int)scale > 127 || big * (long double)(n + m + 2) * scale >= 2147483000.0L) use = false;
     }
     *R = r; *C = c;
     return use;
@@ -854,7 +860,7 @@ int plan_long(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, Lon
     if (wide) R = WIDE_R;
     int tR = 0, tC = 0;
     P->C = 0;
-    if (!wide && pick_tile(n, m, traceback, local, slices, &tR, &tC)) {
+    if (!wide && pick_tile(ctx, sc, n, m, traceback, local, slices, &tR, &tC)) {
         P->R = tR; P->C = tC; P->CB = 1; P->NW = tile_nwt(tR, tC);
         P->n_strips = (uint32_t)((m + 32ull * tR - 1) / (32ull * tR));
         P->smem = tile_smem_bytes(tR, tC, sc->alphabet_size);
@@ -1151,6 +1157,7 @@ bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_
         return false;
     }
     const long double dirBytes = (long double)(n + 64) * (long double)(m + 512) / 4.0L;
+    if (dirBytes < 4.0L * 1073741824.0L && !std::getenv("SA_CKPT_LIMIT_MB")) return false;      // (cudaMemGetInfo costs milliseconds)
     size_t freeB = 0, totalB = 0;
     if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) { cudaGetLastError(); return false; }
     long double limit = 0.6L * (long double)totalB;

@@ -22,9 +22,14 @@
 // tile index + lane, NWT = R*C/16; cell (r, cc) of the tile sits at bit (cc*R + r)*2 of the lane's NWT words.  One
 // 4/8/16-byte store per lane and macro-step, 128..512 contiguous bytes per warp; 0.25 B/cell.
 //
-// SW arg-max (first maximum in row-major order, alignSequenceCPU.cpp:191-192): every tile reduces to its maximum with
-// a VIMNMX3 tree; only when that maximum can still be the alignment-wide arg-max (>= the lane's best and >= the
-// running global maximum) the warp takes a slow path that recomputes the tile to locate the cell.
+// SW arg-max (first maximum in row-major order, alignSequenceCPU.cpp:191-192), without a branch in the macro-step.  The
+// local kernel of 8-row lanes carries 8*H instead of 4*H (tags in bits 0..1, bit 2 zero; tile_scale), so a masked cell value
+// has three free low bits: every cell enters the tile's maximum as KEY = 8*H + (R-1-r) -- one VIADDMNMX per cell, the add is free -- and a
+// larger key means a larger score OR the same score in a smaller row of the lane, which is exactly when a later tile
+// replaces an earlier one.  A lane whose tile key beats its best only keeps the tile's inputs (R left values, C top values,
+// the corner, the macro-step: register selects); the cell is located once, when the strip is over, by recomputing that one
+// tile.  (The first version located on the spot behind a warp vote: the head of a growing local alignment sets a record in
+// almost every tile it crosses, and any branch splits the straight-line macro-step -- the SW sweep cost 2.8x the NW sweep.)
 #pragma once
 #include "sa_tile_host.h"
 
@@ -109,9 +114,9 @@ __device__ __forceinline__ void sts_volatile_u64(const uint32_t saddr, const uns
     asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
 }
 
-// Slow path of the SW arg-max: recompute one tile (plain cells, no tags) and return r*C + cc of the row-major first
+// SW arg-max, once per strip and lane: recompute one tile (plain cells, no tags) and return r*C + cc of the row-major first
 // cell (within the tile's first ncols columns) whose value equals v (R*C when there is none).
-template <int R, int C>
+template <int R, int C, int MASK>
 __device__ __noinline__ int tile_locate(const int v, const int KL, const int KT, const int corner,
                                         const int (&cin)[R], const int (&top)[C], const uint32_t (&pw)[C][(R + 3) / 4], const int ncols)
 {
@@ -126,7 +131,7 @@ __device__ __noinline__ int tile_locate(const int v, const int KL, const int KT,
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int x = __dp4a((int)pw[cc][r >> 2], onehot(r), d);
-            const int cn = viaddmax_relu(t, KT, viaddmax(c[r], KL, x)) & ~3;
+            const int cn = viaddmax_relu(t, KT, viaddmax(c[r], KL, x)) & MASK;
             d = c[r]; t = cn; c[r] = cn;
             if (cn == v && cc < ncols) key = min(key, r * C + cc);
         }
@@ -170,7 +175,10 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
     __syncthreads();
     const unsigned char *profL = profS + lane * RPAD;       // this lane's R profile bytes of letter 0
 
-    const int KL = 2 - SCALE * A.gap, KT = 1 - SCALE * A.gap;
+    constexpr int SC = tile_scale(R, LOCAL);     // the local kernels carry SC*H: log2(SC) free low bits for the arg-max key
+    constexpr int VMASK = ~(SC - 1);
+    static_assert(R <= SC || !LOCAL, "the arg-max key holds the lane's row in the free low bits");
+    const int KL = 2 - SC * A.gap, KT = 1 - SC * A.gap;
     const uint32_t W = gridDim.x * WARPS;
     const int n = (int)A.n, m = (int)A.m;
     const int nTiles = (n + C - 1) / C;          // tiles per lane
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
             const int gi = row0 + i;
             if (gi < m) {
                 const int8_t *srow = S4s + 32 * min((int)A.pattern[gi], alpha - 1);
-                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)srow[a];
+                for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)((SC / SCALE) * srow[a]);      // (host: |SC*S| <= 127)
             } else {
                 for (int a = 0; a < alpha; ++a) profS[a * PS + off] = (unsigned char)0x80;
             }
@@ -260,7 +268,13 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         if (LINKED && A.dbg) { __syncwarp(); if (lane == 0) A.dbg[3 * s + 1] = gtime(); }
 
         int bestv = 0, besti = 0, bestj = 0;
-        int gmCached = 0;                               // lane-local copy of *A.gmax (a lower bound)
+        int bestKey = 0;                                // SW: 8*H + (R-1-row in lane) of the lane's best cell so far
+        // inputs of the lane's best tile so far (straight-line modes): see "SW arg-max" above
+        int snapC[R], snapTop[C], snapCorner = 0, snapK = -1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) snapC[r] = 0;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) snapTop[cc] = 0;
         const bool rowsValid = row0 + lane * R < m;
         const bool hasUp = s > 0, hasDown = s + 1 < A.n_strips;
         // lane 31 publishes the strip's bottom row for the strip below -- or, for the last strip of a row chunk, for
@@ -359,7 +373,6 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         auto text_upkeep = [&](const int k) {
             store_tile_letters(k + 32 + lane, tnext);
             tnext = load_tile_letters(k + 64 + lane);
-            if (LOCAL) gmCached = max(gmCached, *reinterpret_cast<volatile int *>(A.gmax));
             __syncwarp();
         };
 
@@ -407,6 +420,19 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
 #pragma unroll
                 for (int q = 0; q < NPW; ++q) dst[cc][q] = p[q];
             }
+        };
+        // SW: the row-major first cell of the kept tile that holds the lane's best value, as r*C + cc
+        auto locate_snapshot = [&]() -> int {
+            const int kbS = snapK - lane;
+            uint32_t pwS[C][NPW];
+            load_profile(load_tile_letters(kbS), pwS);
+            // (copies: tile_locate is not inlined and takes its arrays by reference -- the kept state itself must stay in registers)
+            int cS[R], tS[C];
+#pragma unroll
+            for (int r = 0; r < R; ++r) cS[r] = snapC[r];
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) tS[cc] = snapTop[cc];
+            return tile_locate<R, C, VMASK>(bestKey & VMASK, KL, KT, snapCorner, cS, tS, pwS, min(C, n - kbS * C));
         };
         load_profile(text_word(0 - lane), pw);
         unsigned long long twN = text_word(1 - lane);
@@ -493,7 +519,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                         const int x = __dp4a((int)pw[cc][r >> 2], onehot(r), dg);         // cD = 4*(D + s)
                         const int mx = viaddmax(left, KL, x);                             // max(cL, cD)
                         const int h = LOCAL ? viaddmax_relu(tp, KT, mx) : viaddmax(tp, KT, mx);
-                        const int cn = h & ~3;
+                        const int cn = h & VMASK;
                         const int bit = 2 * (cc * R + r);
                         deposit_tag(accp[cc][bit >> 5], h, cn, bit & 31);
                         const int cv = (MODE == 3 && cc >= ncols) ? left : cn;             // drain: past the text, keep the last column
@@ -514,10 +540,10 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                 if (LOCAL) {
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) {
-                        int w = v[0][cc];
+                        int w = tmax;          // (two chains per column would be shorter; the tree is off the critical path)
 #pragma unroll
-                        for (int r = 1; r < R; r += 2) w = (r + 1 < R) ? __vimax3_s32(w, v[r][cc], v[r + 1 < R ? r + 1 : r][cc]) : max(w, v[r][cc]);
-                        tmax = max(tmax, w);
+                        for (int r = 0; r < R; ++r) w = viaddmax(v[r][cc], R - 1 - r, w);
+                        tmax = w;
                     }
                 }
             } else {
@@ -532,7 +558,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                                 const int x = __dp4a((int)pw[cc][r >> 2], onehot(r), d);
                                 const int mx = viaddmax(c[r], KL, x);
                                 const int h = LOCAL ? viaddmax_relu(t, KT, mx) : viaddmax(t, KT, mx);
-                                const int cn = h & ~3;
+                                const int cn = h & VMASK;
                                 const int bit = 2 * (cc * R + r);
                                 deposit_tag(accp[cc][bit >> 5], h, cn, bit & 31);
                                 d = c[r]; t = cn; c[r] = cn;
@@ -540,10 +566,8 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                             d0 = topIn[cc];
                             corner = topIn[cc];
                             if (LOCAL) {
-                                int w = c[0];
 #pragma unroll
-                                for (int r = 1; r < R; r += 2) w = (r + 1 < R) ? __vimax3_s32(w, c[r], c[r + 1 < R ? r + 1 : r]) : max(w, c[r]);
-                                tmax = max(tmax, w);
+                                for (int r = 0; r < R; ++r) tmax = viaddmax(c[r], R - 1 - r, tmax);
                             }
                             bot[cc] = c[R - 1];
                         }
@@ -590,15 +614,15 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
             rowW += C;
             if (LINKED && MODE == 1 && A.dbg && kb == 8008 && lane == 31) dbgWrite = gtime();
             if (LOCAL) {
-                const bool cand = active && rowsValid && tmax > 0 && tmax >= bestv && tmax >= gmCached;
-                if (__any_sync(0xffffffffu, cand)) {
-                    if (cand) {
-                        const int key = tile_locate<R, C>(tmax, KL, KT, cornerIn, cin, topIn, pw, ncols);
-                        const int ci = row0 + lane * R + key / C + 1, cj = kb * C + key % C + 1 + (int)A.col0;
-                        if (key < R * C && (tmax > bestv || ci < besti)) { bestv = tmax; besti = ci; bestj = cj; }
-                        if (tmax > gmCached) { atomicMax(A.gmax, tmax); gmCached = tmax; }
-                    }
-                }
+                // tmax is the tile's largest KEY (see the head of the file); scores of 0 never count
+                const bool take = active && rowsValid && tmax > bestKey && tmax >= SC;
+                bestKey = take ? tmax : bestKey;
+                snapK = take ? k : snapK;
+                snapCorner = take ? cornerIn : snapCorner;
+#pragma unroll
+                for (int r = 0; r < R; ++r) snapC[r] = take ? cin[r] : snapC[r];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) snapTop[cc] = take ? topIn[cc] : snapTop[cc];
             }
 #pragma unroll
             for (int cc = 0; cc < C; ++cc)
@@ -676,6 +700,13 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
             if (s == 0 && lane == 0 && A.row_base == 0) A.right_col[0] = LOCAL ? 0 : -SCALE * A.gap * (int)(A.col0 + A.n);
         }
         if (LOCAL) {
+            bestv = (bestKey & VMASK) / (SC / SCALE);          // 4*H, the form the candidates of a strip are reduced in
+            if (bestv > 0) {
+                const int key = locate_snapshot();
+                besti = row0 + lane * R + key / C + 1;
+                bestj = (snapK - lane) * C + key % C + 1 + (int)A.col0;
+            }
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
                 const int ov = __shfl_xor_sync(0xffffffffu, bestv, o);

@@ -1,9 +1,6 @@
 cd /root/repo
-for tag in "" _u2; do
-  export SA_B200_LIB=/root/repo/sequence-alignment-gpu_b200/libsa_b200$tag.so
-  echo "== lib$tag"
-  python bench.py --steps 5 --warmup 3 --no-cpu --c5 off 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
-print('value',round(d['value']),'e2e',round(d['e2e']['value']),'fill ms',round(r['kernel_ms_per_step'],3),'fill gcups',round(r['fill_only_gcups']),'verified',d['verified']['mismatches'])"
-done
+export SA_B200_LIB=/root/repo/sequence-alignment-gpu_b200/libsa_b200_sw.so
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tile or random_pairs or ties or goldens or traceback_variants or gap_penalty or known_answer or identity" 2>&1 | tail -3
+MODE=1 python tools/probe_tile.py 100000 8,2 4,4 strip:8 2>&1 | tail -3
+MODE=1 PROTEIN=1 python tools/probe_tile.py 5000 8,2 4,4 strip:4 2>&1 | tail -3
+python tools/probe_tile.py 100000 8,2 2>&1 | tail -1

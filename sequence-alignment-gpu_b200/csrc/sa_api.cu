@@ -827,7 +827,7 @@ bool pick_tile(const sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t
 
 cudaError_t launch_plan(const LongPlan &P, const LongArgs &A, bool local, int grid, cudaStream_t st, bool wide)
 {
-    if (P.C) return tile_launch(P.R, P.C, local, A.left_col64 || A.right_col64 || A.dbg, A, grid, P.smem, st);
+    if (P.C) return tile_launch(P.R, P.C, local, A.left_col64 || A.right_col64 || (A.dbg && !std::getenv("SA_LONG_DBG_PLAIN")), A, grid, P.smem, st);
     return launch_long(P.R, A, local, grid, P.smem, st, wide);
 }
 
@@ -1645,7 +1645,7 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t nStrips = (uint32_t)((rows + ROWS - 1) / ROWS);
-    const bool linkedKernel = d_left64 || d_right64 || std::getenv("SA_LONG_DBG");
+    const bool linkedKernel = d_left64 || d_right64 || (std::getenv("SA_LONG_DBG") && !std::getenv("SA_LONG_DBG_PLAIN"));
     int occ = S.C ? tile_occupancy(S.R, S.C, false, linkedKernel, S.smem) : occupancy_long(S.R, false, S.smem, linkedKernel);
     if (occ < 1) return SA_ERR_LAUNCH;
     int perSm = std::min(occ, 2);

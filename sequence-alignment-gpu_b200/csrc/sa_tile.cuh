@@ -47,6 +47,9 @@ constexpr int TG = SA_TILE_TG;     // macro-steps per top-row group (prefetch di
 #endif
 constexpr int TG_REQ = SA_TILE_TG_REQ;   // macro-step of a group after which the next group is requested
 constexpr int TEXT_RING = 128;     // tiles of text kept in shared memory per warp
+#ifndef SA_TILE_DBG_PLAIN
+#define SA_TILE_DBG_PLAIN 0        // 1 (dev builds): the per-strip timestamps of SA_LONG_DBG also in the plain kernels
+#endif
 // In-block hand-off (compile-time option, OFF): the strips of one block are neighbours in the chain, so lane 31 can store
 // the {4H, tag} words into a ring of HRING tiles in the NEXT warp's shared memory and that warp's top-row upkeep can poll
 // the ring instead of L2.  Built, bit-exact (the GPU parity tests pass with it) and measured slower on B200: config 3 fills
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
 {
     static_assert((R * C) % 16 == 0, "a tile must fill whole direction words");
     static_assert(C == 2 || C == 4 || C == 8, "tile width");
+    constexpr bool DBG = LINKED || SA_TILE_DBG_PLAIN;
     constexpr int NWT = tile_nwt(R, C);
     static_assert(NWT == 1 || NWT == 2 || NWT == 4, "direction words per lane and macro-step: one vector store");
     constexpr int RPAD = rpad_for(R);
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
 
         // ---- boundary state (left border of the slice) ----
         auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-        if (LINKED && A.dbg && lane == 0) A.dbg[3 * s] = gtime();
+        if (DBG && A.dbg && lane == 0) A.dbg[3 * s] = gtime();
         // linked slices: wait (warp-uniformly, see sa_long.cuh) until the left neighbour's kernel has delivered the word
         auto linked_border = [&](const int gi) -> int {
             const bool need = gi > 0 && gi <= m;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
             else if (A.left_col) corner = gi <= m ? A.left_col[gi] : 0;
             else corner = LOCAL ? 0 : -SCALE * A.gap * (gi + (int)A.row_base);
         }
-        if (LINKED && A.dbg) { __syncwarp(); if (lane == 0) A.dbg[3 * s + 1] = gtime(); }
+        if (DBG && A.dbg) { __syncwarp(); if (lane == 0) A.dbg[3 * s + 1] = gtime(); }
 
         int bestv = 0, besti = 0, bestj = 0;
         int bestKey = 0;                                // SW: 8*H + (R-1-row in lane) of the lane's best cell so far
@@ -317,15 +321,15 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                 const bool mine = lane < TG && col >= 0 && col < n;
                 const uint32_t want = upInBlock ? (ringTagBase | (((uint32_t)(first + lane) >> HRING_SHIFT) & 0xffffffu)) : wantTag;
                 if (upInBlock && mine) ring_load(first + lane);
-                const unsigned long long tSpin = (LINKED && A.dbg) ? gtime() : 0ull;
+                const unsigned long long tSpin = (DBG && A.dbg) ? gtime() : 0ull;
                 bool spun = false;
-                if (LINKED && A.dbg && first == 8001) dbgEnter = tSpin;
+                if (DBG && A.dbg && first == 8001) dbgEnter = tSpin;
                 while (true) {
                     bool ok = true;
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) ok = ok && (!(mine && col + cc < n) || (uint32_t)(pend[cc] >> 32) == want);
                     if (__all_sync(0xffffffffu, ok)) break;
-                    if (LINKED && A.dbg) { spun = true; ++dbgSpins; }
+                    if (DBG && A.dbg) { spun = true; ++dbgSpins; }
                     if (!ok) {
                         if (upInBlock) { if (SA_TILE_RING_SLEEP > 0) __nanosleep(SA_TILE_RING_SLEEP); ring_load(first + lane); }
                         else {
@@ -335,8 +339,8 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                         }
                     }
                 }
-                if (LINKED && A.dbg && spun) { dbgSpinNs += gtime() - tSpin; ++dbgStalls; if (first <= 33) ++dbgRampStalls; }
-                if (LINKED && A.dbg && first == 8001) dbgExit = gtime();
+                if (DBG && A.dbg && spun) { dbgSpinNs += gtime() - tSpin; ++dbgStalls; if (first <= 33) ++dbgRampStalls; }
+                if (DBG && A.dbg && first == 8001) dbgExit = gtime();
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc) tv[cc] = (int)(uint32_t)pend[cc];
             } else {
@@ -612,7 +616,6 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                                                      ((unsigned long long)(ringTagBase | (((uint32_t)kb >> HRING_SHIFT) & 0xffffffu)) << 32) | (uint32_t)bot[cc]);
             }
             rowW += C;
-            if (LINKED && MODE == 1 && A.dbg && kb == 8008 && lane == 31) dbgWrite = gtime();
             if (LOCAL) {
                 // tmax is the tile's largest KEY (see the head of the file); scores of 0 never count
                 const bool take = active && rowsValid && tmax > bestKey && tmax >= SC;
@@ -634,12 +637,12 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         // (the last tile of a lane -- full or partial -- always belongs to the drain, which parks the final column)
         const int nStraight = nTiles - 1;
         const int kRamp = nStraight >= 32 ? 32 : 0;
-        if (LINKED && A.dbg && lane == 0) A.dbg[3 * A.n_strips + 4 * s] = gtime();
+        if (DBG && A.dbg && lane == 0) A.dbg[3 * A.n_strips + 4 * s] = gtime();
         for (int k = 0; k < kEnd; k += TG) {
             top_upkeep(k + 1);
             if (SA_TILE_HANDOFF) ring_space(k);
             if (k >= 32 && (k & 31) == 0) text_upkeep(k);
-            if (LINKED && A.dbg && lane == 0) {
+            if (DBG && A.dbg && lane == 0) {
                 if (k == 32) A.dbg[3 * A.n_strips + 4 * s + 1] = gtime();
                 if (k + TG > nStraight && k < nStraight + TG) A.dbg[3 * A.n_strips + 4 * s + 2] = gtime();
                 if (k + TG >= kEnd) A.dbg[3 * A.n_strips + 4 * s + 3] = gtime();
@@ -676,14 +679,14 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         }
 
         // ---- strip results ----
-        if (LINKED && A.dbg && lane == 0) {
+        if (DBG && A.dbg && lane == 0) {
             A.dbg[3 * s + 2] = gtime();
             unsigned long long *x = A.dbg + 7 * (size_t)A.n_strips + 4 * (size_t)s;
             x[0] = dbgSpins; x[1] = dbgSpinNs; x[2] = dbgStalls; x[3] = dbgRampStalls;
             unsigned long long *y = A.dbg + 11 * (size_t)A.n_strips + 2 * (size_t)s;
             y[0] = dbgEnter; y[1] = dbgExit;
         }
-        if (LINKED && A.dbg && lane == 31) A.dbg[13 * (size_t)A.n_strips + s] = dbgWrite;
+        if (DBG && A.dbg && lane == 31) A.dbg[13 * (size_t)A.n_strips + s] = dbgWrite;
         if (LINKED && A.right_col64) {          // linked slices: straight into the right neighbour's memory
 #pragma unroll
             for (int r = 0; r < R; ++r) {

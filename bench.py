@@ -298,6 +298,23 @@ def verify_single(args, w, got):
     return 1, int(got.key() != want.key()), "reference" if isinstance(eng, Reference) else "port"
 
 
+def device_for_rank(local_rank, world):
+    """CUDA device of a local rank.  The GPUs of an HGX box hang off two host bridges (devices 0..D/2-1 and D/2..D-1);
+    the end-to-end path moves 1.24 GB per 1 M pairs through the host, so a run on fewer ranks than devices spreads its
+    ranks over both halves (0, D/2, 1, D/2+1, ...) instead of filling the first one.  Measured on 8 x B200: four ranks on
+    devices 0-3 copy at 11.3 + 12.0 GB/s each, two ranks at 17.6 + 18.7 GB/s.  NVLink is all-to-all (NV18), so the order
+    does not matter to the linked slices of config 5.  SA_BENCH_DEVICE_ORDER=linear keeps device = local rank."""
+    try:
+        import torch
+        ndev = torch.cuda.device_count()
+    except Exception:
+        return local_rank
+    if os.environ.get("SA_BENCH_DEVICE_ORDER") == "linear" or ndev < 4 or ndev % 2 or world >= ndev or local_rank >= ndev:
+        return local_rank
+    half = ndev // 2
+    return (local_rank // 2) + half * (local_rank % 2)
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -490,6 +507,7 @@ def run_ours(args, rank, world, local_rank):
                 scaling=(args.scaling if w["kind"] == "batch" else "weak"),
                 vs_baseline=None, dtype=mode, data="synthetic" if args.workload in ("c3", "c4") else "reference data/ files",
                 config=dict(workload=w["name"], l2=l2_note, cells_per_step=cells_all, rank0_cells_per_step=w["cells"],
+                            devices=[device_for_rank(r, world) for r in range(world)],
                             parallelism=("one batch cut into cell-balanced contiguous ranges, one per rank, no collective" if w["kind"] == "batch" and args.scaling == "strong"
                                          else "every rank aligns its own batch, no collective" if w["kind"] == "batch" else "replicas only")),
                 e2e=dict(value=e2e_value, unit="GCUPS", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -564,7 +582,7 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = device_for_rank(int(os.environ.get("LOCAL_RANK", "0")), world)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

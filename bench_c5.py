@@ -151,7 +151,8 @@ def main():
     from __graft_entry__ import load_package
     sa = load_package()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    from bench import device_for_rank
+    local_rank = device_for_rank(int(os.environ.get("LOCAL_RANK", 0)), world)
     if not torch.cuda.is_available():
         raise SystemExit("bench_c5.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)

@@ -1622,7 +1622,7 @@ int sa_strip_linked_status(sa_context *ctx, void *stream)
     SA_TRY(cudaMemcpyAsync(&flag, ctx->misc.as<char>() + 56, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream), SA_ERR_COPY);
     SA_TRY(cudaStreamSynchronize((cudaStream_t)stream), SA_ERR_LAUNCH);
     if (const char *path = std::getenv("SA_LONG_DBG")) {
-        std::vector<unsigned long long> h((size_t)ctx->strip.dbg_strips * 16);
+        std::vector<unsigned long long> h((size_t)ctx->strip.dbg_strips * (16 + 128));      // 16 scalars + 64 {group, ns} stall events per strip
         if (!h.empty() && cudaMemcpy(h.data(), ctx->tbbuf.p, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
             char name[512];
             std::snprintf(name, sizeof name, "%s.dev%d", path, ctx->device);
@@ -1675,8 +1675,8 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);
     if (d_left64 || d_right64) SA_TRY(cudaMemsetAsync(A.abort_flag, 0, 4, st), SA_ERR_LAUNCH);
     if (std::getenv("SA_LONG_DBG")) {          // dev aid: per-strip timestamps, dumped by sa_strip_linked_status
-        SA_TRY(ctx->tbbuf.reserve((size_t)nStrips * 128 + 64), SA_ERR_MEMORY);
-        SA_TRY(cudaMemsetAsync(ctx->tbbuf.p, 0, (size_t)nStrips * 128, st), SA_ERR_LAUNCH);
+        SA_TRY(ctx->tbbuf.reserve((size_t)nStrips * (128 + 1024) + 64), SA_ERR_MEMORY);
+        SA_TRY(cudaMemsetAsync(ctx->tbbuf.p, 0, (size_t)nStrips * (128 + 1024), st), SA_ERR_LAUNCH);
         A.dbg = ctx->tbbuf.as<unsigned long long>();
         ctx->strip.dbg_strips = nStrips;
     }

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) pend[cc] = 0;
         unsigned long long dbgSpins = 0, dbgSpinNs = 0, dbgStalls = 0, dbgRampStalls = 0, dbgEnter = 0, dbgExit = 0, dbgWrite = 0;      // (LINKED + dbg only)
+        uint32_t dbgEvents = 0;
         // group with first tile `first`: lanes q < TG own tile first + q (window slot (first + q) % (2*TG))
         auto request_top = [&](const int first) {
             if (upInBlock) return;                       // shared memory: read when needed
@@ -339,7 +340,16 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                         }
                     }
                 }
-                if (DBG && A.dbg && spun) { dbgSpinNs += gtime() - tSpin; ++dbgStalls; if (first <= 33) ++dbgRampStalls; }
+                if (DBG && A.dbg && spun) {
+                    const unsigned long long dt = gtime() - tSpin;
+                    dbgSpinNs += dt; ++dbgStalls; if (first <= 33) ++dbgRampStalls;
+                    // the first 64 stalls after the ramp: {first tile of the group, ns}
+                    if (first > 33 && dbgEvents < 64 && lane == 0) {
+                        unsigned long long *ev = A.dbg + 16 * (size_t)A.n_strips + 128 * (size_t)s + 2 * dbgEvents;
+                        ev[0] = (unsigned long long)first; ev[1] = dt;
+                    }
+                    if (first > 33) ++dbgEvents;
+                }
                 if (DBG && A.dbg && first == 8001) dbgExit = gtime();
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc) tv[cc] = (int)(uint32_t)pend[cc];

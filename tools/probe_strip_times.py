@@ -33,7 +33,8 @@ for rep in range(3):
     al.strip_fill_rows(0, len(p), 0, right.data_ptr(), 0, 0)
     al.strip_linked_status()
 raw = np.fromfile(dbg + ".dev0", dtype=np.uint64)
-S = len(raw) // 16
+S = len(raw) // (16 + 128)
+events = raw[16 * S:].reshape(S, 64, 2).astype(np.int64)      # the first 64 top-row stalls after the ramp: {first tile of the group, ns}
 ts = raw[:3 * S].reshape(S, 3).astype(np.int64)
 ex = raw[3 * S:7 * S].reshape(S, 4).astype(np.int64)          # loop start, k == 32, first drain group, last group
 cnt = raw[7 * S:11 * S].reshape(S, 4).astype(np.int64)        # spin iterations, ns spent spinning, groups that stalled, of those in the ramp
@@ -63,4 +64,11 @@ if S > 1:
         print(f"  lag per strip at {name}: median {np.median(np.diff(col)) / 1e3:.2f} us")
     d = np.diff(ends)
     print(f"end-to-end lag per strip: median {np.median(d):.2f} us, mean {d.mean():.2f} us, max {d.max():.2f} us")
+for s_ in sorted(set([1, 2, 3, 4, 5, S // 2, S - 1])):
+    if 0 < s_ < S:
+        ev = events[s_]
+        ev = ev[ev[:, 0] > 0]
+        print(f"  strip {s_}: stalls after the ramp (group start tile : ns) " + " ".join(f"{a}:{b}" for a, b in ev[:24]))
+        if len(ev) > 2:
+            print(f"     gaps between stalled groups (tiles): {np.diff(ev[:, 0])[:24].tolist()}   median stall {np.median(ev[:, 1]):.0f} ns")
 al.close()

@@ -1165,7 +1165,8 @@ bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_
     if (dirBytes <= limit) return false;
     // chunks as tall as the memory allows, all of the same height: a chunk is one launch of the long-pair kernel, and a
     // wide, low matrix keeps few strips busy (1 000 000 columns: 65 536 rows fill at 0.9 TCUPS, 390 000 rows at 2.7)
-    long double chunkBytes = std::min(limit, 0.5L * (long double)totalB);
+    // (what is free now plus what the context already holds for directions: other users of the device count)
+    long double chunkBytes = std::min(std::min(limit, 0.5L * (long double)totalB), 0.85L * ((long double)freeB + (long double)ctx->dirs.cap));
     if (const char *e = std::getenv("SA_CKPT_CHUNK_MB")) chunkBytes = (long double)std::atoll(e) * 1048576.0L;
     const uint64_t rowsMax = std::max<uint64_t>(1024, (uint64_t)(chunkBytes * 4.0L / (long double)(n + 64)));
     const uint64_t K = (m + rowsMax - 1) / rowsMax;

@@ -144,3 +144,22 @@ def test_two_rank_gloo_column_slices(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert '"ok": true' in outs[0][0]
+
+
+def test_bench_spreads_ranks_over_both_host_bridges(monkeypatch):
+    """bench.py maps local ranks to devices 0, D/2, 1, D/2+1, ... when a run uses fewer ranks than the box has GPUs
+    (the end-to-end path is bound by the host side of PCIe, and the GPUs hang off two host bridges)."""
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    fake = types.SimpleNamespace(cuda=types.SimpleNamespace(device_count=lambda: 8))
+    monkeypatch.setitem(sys.modules, "torch", fake)
+    assert [bench.device_for_rank(r, 4) for r in range(4)] == [0, 4, 1, 5]
+    assert [bench.device_for_rank(r, 2) for r in range(2)] == [0, 4]
+    assert [bench.device_for_rank(r, 8) for r in range(8)] == list(range(8))
+    monkeypatch.setenv("SA_BENCH_DEVICE_ORDER", "linear")
+    assert [bench.device_for_rank(r, 4) for r in range(4)] == [0, 1, 2, 3]
+    monkeypatch.delenv("SA_BENCH_DEVICE_ORDER")
+    fake.cuda.device_count = lambda: 2
+    assert [bench.device_for_rank(r, 2) for r in range(2)] == [0, 1]

@@ -1059,7 +1059,7 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
 // Twice the fill work, directions for ONE chunk in memory: 1 M x 0.95 M needs 16 GB at 64 k rows instead of 250 GB.
 // Everything is enqueued on `st` without a host synchronisation.  Results land where enqueue_long puts them.
 int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, uint64_t n, const uint8_t *d_pat,
-                              uint64_t m, char *d_outT, char *d_outP, uint64_t cap, uint64_t chunk_hint, cudaStream_t st)
+                              uint64_t m, char *d_outT, char *d_outP, uint64_t cap, uint64_t chunk_hint, bool traceback, cudaStream_t st)
 {
     if (sc->mode != SA_GLOBAL) return SA_ERR_MEMORY;
     LongPlan P;
@@ -1122,7 +1122,8 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
     for (uint64_t c = 0; c < K; ++c) { rc = fill_chunk(c, true); if (rc) return rc; }
     cudaEventRecord(e1, st);
     cudaEventRecord(e2, st);          // (the second pass interleaves fills and tracebacks: it is accounted as traceback time)
-    for (uint64_t c = K; c-- > 0;) {
+    // score only (sa_fill_only): the first pass is the whole job
+    for (uint64_t c = traceback ? K : 0; c-- > 0;) {
         if (c + 1 < K) { rc = fill_chunk(c, false); if (rc) return rc; }
         const uint64_t row0 = c * chunk, rows = std::min<uint64_t>(chunk, m - row0);
         LongPlan Pc = P;
@@ -1150,7 +1151,8 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
 // SA_CKPT_CHUNK_MB: direction bytes of one row chunk (default: half the device memory).
 bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, bool traceback, uint64_t *chunk_rows)
 {
-    if (!traceback || sc->mode != SA_GLOBAL || ctx->wide) return false;
+    (void)traceback;                      // (a score-only call of that size runs the first pass alone)
+    if (sc->mode != SA_GLOBAL || ctx->wide) return false;
     if (const char *e = std::getenv("SA_CKPT_ROWS")) {
         const long long r = std::atoll(e);
         if (r > 0 && (uint64_t)r < m) { *chunk_rows = (uint64_t)r; return true; }
@@ -1180,7 +1182,7 @@ int enqueue_long_auto(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_te
 {
     uint64_t chunkRows = 0;
     if (want_checkpoints(ctx, sc, n, m, traceback, &chunkRows))
-        return enqueue_long_checkpointed(ctx, sc, d_text, n, d_pat, m, d_outT, d_outP, cap, chunkRows, st);
+        return enqueue_long_checkpointed(ctx, sc, d_text, n, d_pat, m, d_outT, d_outP, cap, chunkRows, traceback, st);
     return enqueue_long(ctx, sc, d_text, n, d_pat, m, d_outT, d_outP, cap, traceback, st);
 }
 

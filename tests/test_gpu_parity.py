@@ -840,6 +840,7 @@ def test_checkpointed_traceback_vs_oracle(aligner, oracle, force_path, monkeypat
             ident = sum(1 for a, b in zip(want.aligned_text, want.aligned_pattern) if a == b)
             gaps = sum(1 for a, b in zip(want.aligned_text, want.aligned_pattern) if a == ord("-") or b == ord("-"))
             assert st == (ident, gaps), (variant, len(t), len(p))
+            assert aligner.fill_only(0, alpha, mat, gap, t, p)[0] == want.score          # score only: the first pass alone
             # a local alignment of the same pair is untouched by the switch
             assert_same(aligner.align(1, alpha, mat, gap, t, p), oracle.align(1, alpha, mat, gap, t, p), (variant, "local"))
 

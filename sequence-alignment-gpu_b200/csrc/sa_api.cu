@@ -1013,7 +1013,8 @@ int enqueue_long(sa_context *ctx, const sa_scoring *sc, const uint8_t *d_text, u
     A.score = d_score; A.cand_v = d_cv; A.cand_i = d_ci; A.cand_j = d_cj;
     A.tag_base = (uint32_t)ctx->epoch << 21;
     A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
-    SA_TRY(cudaMemsetAsync(A.gmax, 0, 4, st), SA_ERR_LAUNCH);
+    A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);
+    SA_TRY(cudaMemsetAsync(A.gmax, 0, 12, st), SA_ERR_LAUNCH);          // gmax, (unused), abort flag
     cudaEvent_t e0 = next_event(ctx), e1 = next_event(ctx), e2 = next_event(ctx), e3 = next_event(ctx);
     cudaEventRecord(e0, st);
     SA_TRY(launch_plan(P, A, local, P.grid, st, ctx->wide), SA_ERR_LAUNCH);
@@ -1080,6 +1081,7 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
     const int ncol = (int)n;
     SA_TRY(cudaMemcpyAsync(d_col, &ncol, 4, cudaMemcpyHostToDevice, st), SA_ERR_COPY);
     SA_TRY(cudaMemsetAsync(d_emitted, 0, 24, st), SA_ERR_LAUNCH);
+    SA_TRY(cudaMemsetAsync(ctx->misc.as<char>() + 56, 0, 4, st), SA_ERR_LAUNCH);          // abort flag of the fills
     auto ckrow = [&](uint64_t c) { return ctx->ckpt.as<int>() + (size_t)c * n; };          // top row of chunk c (c >= 1)
     int32_t *d_scratch_score = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 100);   // pass 2: a chunk's own corner value is not the score
     auto fill_chunk = [&](uint64_t c, bool keepBottom) -> int {
@@ -1107,6 +1109,7 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
         A.score = keepBottom ? d_score : d_scratch_score;
         A.tag_base = (uint32_t)ctx->epoch << 21;
         A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
+        A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);
         SA_TRY(launch_plan(P, A, false, grid, st, ctx->wide), SA_ERR_LAUNCH);
         ctx->timing.kernel_launches++;
         if (A.bottom_row) {
@@ -1438,12 +1441,14 @@ static int align_single(sa_context *ctx, const sa_scoring *sc, const uint8_t *te
                                ctx->doutT.as<char>(), ctx->doutP.as<char>(), slot, traceback, st);
         if (rc) return rc;
         cudaEventRecord(ctx->ev[3], st);
-        uint64_t hr[4]; int32_t hs = 0;
+        uint64_t hr[4]; int32_t hs = 0, hflag = 0;
         SA_TRY(cudaMemcpyAsync(hr, ctx->misc.p, sizeof hr, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         SA_TRY(cudaMemcpyAsync(&hs, ctx->misc.as<char>() + 32, 4, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
+        SA_TRY(cudaMemcpyAsync(&hflag, ctx->misc.as<char>() + 56, 4, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         unsigned long long hst[2] = {0, 0};
         if (traceback) SA_TRY(cudaMemcpyAsync(hst, ctx->stats_src, 16, cudaMemcpyDeviceToHost, st), SA_ERR_COPY);
         SA_TRY(cudaStreamSynchronize(st), SA_ERR_LAUNCH);
+        if (hflag) return SA_ERR_LAUNCH;          // a strip's watchdog fired (sa_tile.cuh): the launch gave up instead of hanging
         ctx->last_stats.identity = hst[0]; ctx->last_stats.gaps = hst[1]; ctx->have_stats = traceback;
         hres.score = hs; hres.aln_len = hr[0]; hres.start_text = hr[1]; hres.start_pattern = hr[2];
         hoff = slot - hr[0];
@@ -1676,7 +1681,7 @@ static int strip_launch(sa_context *ctx, uint64_t row0, uint64_t rows, const int
     A.row_base = (uint32_t)row0; A.top_row = d_top_row; A.bottom_row = last ? nullptr : d_bottom_row;
     A.left_col64 = d_left64; A.right_col64 = d_right64; A.xtag = xtag;
     A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);
-    if (d_left64 || d_right64) SA_TRY(cudaMemsetAsync(A.abort_flag, 0, 4, st), SA_ERR_LAUNCH);
+    SA_TRY(cudaMemsetAsync(A.abort_flag, 0, 4, st), SA_ERR_LAUNCH);
     if (std::getenv("SA_LONG_DBG")) {          // dev aid: per-strip timestamps, dumped by sa_strip_linked_status
         SA_TRY(ctx->tbbuf.reserve((size_t)nStrips * (128 + 1024) + 64), SA_ERR_MEMORY);
         SA_TRY(cudaMemsetAsync(ctx->tbbuf.p, 0, (size_t)nStrips * (128 + 1024), st), SA_ERR_LAUNCH);

@@ -47,6 +47,9 @@ constexpr int TG = SA_TILE_TG;     // macro-steps per top-row group (prefetch di
 #endif
 constexpr int TG_REQ = SA_TILE_TG_REQ;   // macro-step of a group after which the next group is requested
 constexpr int TEXT_RING = 128;     // tiles of text kept in shared memory per warp
+#ifndef SA_TILE_WATCHDOG
+#define SA_TILE_WATCHDOG 0
+#endif
 #ifndef SA_TILE_DBG_PLAIN
 #define SA_TILE_DBG_PLAIN 0        // 1 (dev builds): the per-strip timestamps of SA_LONG_DBG also in the plain kernels
 #endif
@@ -301,6 +304,9 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
         for (int cc = 0; cc < C; ++cc) pend[cc] = 0;
         unsigned long long dbgSpins = 0, dbgSpinNs = 0, dbgStalls = 0, dbgRampStalls = 0, dbgEnter = 0, dbgExit = 0, dbgWrite = 0;      // (LINKED + dbg only)
         uint32_t dbgEvents = 0;
+#if SA_TILE_WATCHDOG
+        bool gaveUp = false;                            // the watchdog of the top-row wait fired (this launch's results are void)
+#endif
         // group with first tile `first`: lanes q < TG own tile first + q (window slot (first + q) % (2*TG))
         auto request_top = [&](const int first) {
             if (upInBlock) return;                       // shared memory: read when needed
@@ -325,11 +331,31 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
                 const unsigned long long tSpin = (DBG && A.dbg) ? gtime() : 0ull;
                 bool spun = false;
                 if (DBG && A.dbg && first == 8001) dbgEnter = tSpin;
+#if SA_TILE_WATCHDOG
+                unsigned polls = 0;
+                long long tWait = 0;
+#endif
                 while (true) {
                     bool ok = true;
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) ok = ok && (!(mine && col + cc < n) || (uint32_t)(pend[cc] >> 32) == want);
+#if SA_TILE_WATCHDOG
+                    if (__all_sync(0xffffffffu, ok) || gaveUp) break;
+                    // Watchdog (compile-time option, off): the cooperative launch keeps every producer resident and a
+                    // strip that gave up on its left neighbour GPU (linked_border) still publishes its row, so this wait
+                    // cannot deadlock by construction.  With -DSA_TILE_WATCHDOG=1 a wait that outlives ~20 s raises the
+                    // call's abort flag (the host then reports SA_ERR_LAUNCH) and every other wait of the launch runs
+                    // out.  Off because the extra state costs the straight-line macro-steps 2.5-4 % (config 3: 10.48
+                    // against 10.23 ms) -- this kernel's schedule is that sensitive.
+                    if (polls == 0) tWait = clock64();
+                    if ((++polls & 0x3fffu) == 0 && A.abort_flag) {
+                        bool dead = *reinterpret_cast<volatile int *>(A.abort_flag) != 0;
+                        if (clock64() - tWait > 40000000000ll) { atomicExch(A.abort_flag, 1); dead = true; }
+                        if (__any_sync(0xffffffffu, dead)) { gaveUp = true; break; }
+                    }
+#else
                     if (__all_sync(0xffffffffu, ok)) break;
+#endif
                     if (DBG && A.dbg) { spun = true; ++dbgSpins; }
                     if (!ok) {
                         if (upInBlock) { if (SA_TILE_RING_SLEEP > 0) __nanosleep(SA_TILE_RING_SLEEP); ring_load(first + lane); }

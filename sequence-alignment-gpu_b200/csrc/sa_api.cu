@@ -1771,7 +1771,11 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / perPair));
     const char *ps = std::getenv("SA_BATCH_PIPELINE");
     const bool pipeline = !(ps && ps[0] == '0') && b->n_pairs >= 8192;
-    if (pipeline) chunk = std::min<uint64_t>(chunk, (b->n_pairs + 3) / 4);      // at least 4 chunks to overlap
+    // at least 4 chunks to overlap; small batches 2 -- every chunk costs ~0.15 ms of binning and kernel tails
+    // (125 000 pairs: 3.51 / 3.55 / 3.62 / 3.79 ms with 2 / 3 / 4 / 6 chunks; 250 000: 7.18 / 6.96 / 6.85 / 6.86)
+    uint64_t minChunks = b->n_pairs >= 200000 ? 4 : 2;
+    if (const char *e = std::getenv("SA_BATCH_MIN_CHUNKS")) { const int v = std::atoi(e); if (v >= 1) minChunks = (uint64_t)v; }
+    if (pipeline) chunk = std::min<uint64_t>(chunk, (b->n_pairs + minChunks - 1) / minChunks);
     chunk = std::min<uint64_t>(chunk, b->n_pairs);
     chunk = (b->n_pairs + (b->n_pairs + chunk - 1) / chunk - 1) / ((b->n_pairs + chunk - 1) / chunk);      // equal chunks, no stub at the end
     for (int k = 0; k < (pipeline ? 2 : 1); ++k) {

@@ -240,7 +240,7 @@ bool cfg_exists(int R, int L)
 
 size_t batch_task_stride(const BatchCfg &c, uint32_t max_n, int packed)
 {
-    if (packed == 2) return (((size_t)max_n + 31 + 3) / 4) * 32 * pq_for(c.R);       // quad layout (sa_batch16_sw.cuh)
+    if (packed == 2) return (((size_t)max_n + 31 + 7) / 8) * 2 * 32 * pq_for(c.R);   // quad layout (sa_batch16_sw.cuh), whole octets of columns
     const int CB = packed ? cb16_for(c.R) : cb_for(c.R), NW = c.R * CB / (packed ? 8 : 16);
     const size_t nblocks = ((size_t)max_n + c.L - 1 + CB - 1) / CB;
     return nblocks * NW * 32;

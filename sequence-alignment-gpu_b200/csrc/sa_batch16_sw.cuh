@@ -11,13 +11,14 @@
 //   * the text is fetched as one aligned word per FOUR steps (funnel-shifted by the lane's byte
 //     phase) instead of a byte per step.
 //   * the arg-max (reference: first maximum in row-major order, alignSequenceCPU.cpp:150-168) is
-//     tracked per QUAD of four columns: each step only reduces the column to its maximum
-//     (VIMNMX3 tree); once per quad the lane compares the quad maximum with its best and, on a
-//     strict improvement, keeps the quad's START state (R cells + the 4 tops + the diagonal) with
-//     one PRMT per register -- branch-free, the two pairs of the word select independently.
-//     After the sweep the winning quad is replayed (4 columns, once per task) to locate the exact
-//     first cell.  Equal maxima in different quads take a slow path that replays both; it is only
-//     entered while the value is the pair-wide maximum so far (one REDUX.MAX per half and quad).
+//     tracked per OCTET of eight columns (two quads of the direction layout): each step only reduces
+//     the column to its maximum (VIMNMX3 tree); once per octet the lane compares the octet maximum
+//     with its best and, on a strict improvement, keeps the octet's START state (R cells + the 8 tops
+//     + the diagonal) with one PRMT per register -- branch-free, the two pairs of the word select
+//     independently.  After the sweep the winning octet is replayed (8 columns, once per task) to
+//     locate the exact first cell.  Equal maxima in different octets take a slow path that replays
+//     both; it is only entered while the value is the pair-wide maximum so far (one REDUX.MAX per half
+//     and octet).  (Per quad the copies and selects of this bookkeeping were 8 % of the loop.)
 //
 // Results are bit-identical to the s32 kernel; tests/test_gpu_parity.py compares all three.
 #pragma once
@@ -46,10 +47,11 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t saddr)
 // line on almost every step (the warp-step-major layout), which is what bounds the batch traceback.
 __host__ __device__ constexpr int pq_for(int R) { return (R + 1) / 2 <= 2 ? 2 : (R + 1) / 2 <= 4 ? 4 : 8; }
 
+constexpr int NKEEP = 8;         // columns per arg-max bookkeeping interval (two quads)
 template <int R>
 struct Quad16 {
-    uint32_t c[R];       // the lane's R cells in the column before the quad (packed A|B)
-    uint32_t top[4];     // the value above the lane's first row in the quad's four columns
+    uint32_t c[R];       // the lane's R cells in the column before the octet (packed A|B)
+    uint32_t top[NKEEP]; // the value above the lane's first row in the octet's eight columns
     uint32_t diag;       // ... and in the column before
 };
 
@@ -70,11 +72,11 @@ __device__ __forceinline__ void sw16_column_plain(uint32_t (&c)[R], uint32_t top
     }
 }
 
-// Re-run the four columns of a quad and return, per half, the key 4*row + column of the row-major
+// Re-run the eight columns of an octet and return, per half, the key 8*row + column of the row-major
 // first cell equal to that half of v2 (0xFFFF when there is none).
-//   lettersA4/B4: the four letters of the quad (byte k = column k), sprofA/B: the lane's profile base.
+//   lettersA/B: the eight letters of the octet (byte k = column k), sprofA/B: the lane's profile base.
 template <int R>
-__device__ __noinline__ uint32_t replay_quad16(const Quad16<R> s, const uint32_t v2, const uint32_t lettersA4, const uint32_t lettersB4,
+__device__ __noinline__ uint32_t replay_quad16(const Quad16<R> s, const uint32_t v2, const unsigned long long lettersA, const unsigned long long lettersB,
                                                const uint32_t sprofA, const uint32_t sprofB, const uint32_t KL2, const uint32_t KT2)
 {
     constexpr int NPW = (R + 3) / 4;
@@ -86,9 +88,11 @@ __device__ __noinline__ uint32_t replay_quad16(const Quad16<R> s, const uint32_t
     const int vA = half_of<0>(v2), vB = half_of<1>(v2);
     int keyA = 0xFFFF, keyB = 0xFFFF;
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t top = k == 0 ? s.top[0] : k == 1 ? s.top[1] : k == 2 ? s.top[2] : s.top[3];
-        const uint32_t la = (lettersA4 >> (8 * k)) & 0xffu, lb = (lettersB4 >> (8 * k)) & 0xffu;
+    for (int k = 0; k < NKEEP; ++k) {
+        uint32_t top = s.top[0];
+#pragma unroll
+        for (int kk = 1; kk < NKEEP; ++kk) top = (k == kk) ? s.top[kk] : top;
+        const uint32_t la = (uint32_t)(lettersA >> (8 * k)) & 0xffu, lb = (uint32_t)(lettersB >> (8 * k)) & 0xffu;
         uint32_t pa[NPW], pb[NPW];
 #pragma unroll
         for (int q = 0; q < NPW; ++q) { pa[q] = lds_u32(sprofA + la * PS + 4 * q); pb[q] = lds_u32(sprofB + lb * PS + 4 * q); }
@@ -96,8 +100,8 @@ __device__ __noinline__ uint32_t replay_quad16(const Quad16<R> s, const uint32_t
         diag = top;
 #pragma unroll
         for (int r = R - 1; r >= 0; --r) {
-            if (half_of<0>(c[r]) == vA) keyA = min(keyA, 4 * r + k);
-            if (half_of<1>(c[r]) == vB) keyB = min(keyB, 4 * r + k);
+            if (half_of<0>(c[r]) == vA) keyA = min(keyA, NKEEP * r + k);
+            if (half_of<1>(c[r]) == vB) keyB = min(keyB, NKEEP * r + k);
         }
     }
     return (uint32_t)keyA | ((uint32_t)keyB << 16);
@@ -239,7 +243,8 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
         __syncwarp();
         const int nG = max(nA, nB);
         const int nSteps = nG + 31;
-        const int nQuads = (nSteps + 3) >> 2;
+        const int nOct = (nSteps + NKEEP - 1) / NKEEP;          // whole octets (two quads): the bookkeeping interval
+        const int nQuads = 2 * nOct;
         // texts: TPAD sentinels, the letters, sentinels up to the last byte any quad can touch
         for (int j = l; j < 4 * nQuads + TPAD + 8; j += 32) {
             const int t = j - TPAD;
@@ -268,65 +273,77 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
         const uint32_t G2 = (uint32_t)((SCALE * A.gap) & 0xffff) * 0x10001u;
         uint32_t border = 0u;                         // NW: 4*H(0, column) of the step, both halves
         uint32_t best2 = 0u;
-        int bestqA = 0, bestqB = 0;
+        int bestqA = 0, bestqB = 0;                   // octet of the kept state, per half
         Quad16<R> snap;
 #pragma unroll
         for (int r = 0; r < R; ++r) snap.c[r] = 0u;
-        snap.top[0] = snap.top[1] = snap.top[2] = snap.top[3] = 0u; snap.diag = 0u;
+#pragma unroll
+        for (int k = 0; k < NKEEP; ++k) snap.top[k] = 0u;
+        snap.diag = 0u;
 
         uint32_t *dptr = dirs + (size_t)task * A.task_stride + lane * PQ;
         uint32_t pTextA = stextA + 4 * word0, pTextB = stextB + 4 * word0;
         uint32_t wA0 = lds_u32(pTextA), wB0 = lds_u32(pTextB);
+        // the eight letters of octet o for this lane (byte k = column 8*o + k)
+        auto octet_letters = [&](const uint32_t stext, const int o) -> unsigned long long {
+            const int a = NKEEP * o - l + TPAD;
+            const uint32_t w0 = lds_u32(stext + (a & ~3)), w1 = lds_u32(stext + (a & ~3) + 4), w2 = lds_u32(stext + (a & ~3) + 8);
+            return (unsigned long long)__funnelshift_r(w0, w1, 8 * (a & 3)) | ((unsigned long long)__funnelshift_r(w1, w2, 8 * (a & 3)) << 32);
+        };
 
-        for (int q = 0; q < nQuads; ++q) {
-            pTextA += 4; pTextB += 4;
-            const uint32_t wA1 = lds_u32(pTextA), wB1 = lds_u32(pTextB);
-            const uint32_t la4 = __funnelshift_r(wA0, wA1, 8 * phase), lb4 = __funnelshift_r(wB0, wB1, 8 * phase);
-            wA0 = wA1; wB0 = wB1;
-
+        for (int o = 0; o < nOct; ++o) {
             Quad16<R> cur;
 #pragma unroll
             for (int r = 0; r < R; ++r) cur.c[r] = c[r];
             cur.diag = prevTop;
-            uint32_t cm[4];
-            uint32_t acc[PQ];
+            uint32_t cm[NKEEP];
 #pragma unroll
-            for (int w = 0; w < PQ; ++w) acc[w] = 0;
+            for (int h = 0; h < NKEEP / 4; ++h) {
+                pTextA += 4; pTextB += 4;
+                const uint32_t wA1 = lds_u32(pTextA), wB1 = lds_u32(pTextB);
+                const uint32_t la4 = __funnelshift_r(wA0, wA1, 8 * phase), lb4 = __funnelshift_r(wB0, wB1, 8 * phase);
+                wA0 = wA1; wB0 = wB1;
+                uint32_t acc[PQ];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
-                if (!LOCAL) border = __vsub2(border, G2);
-                const uint32_t top = (l == 0) ? (LOCAL ? 0u : border) : up;
-                const uint32_t KLk = (LOCAL || 4 * q + k >= l) ? KL2 : 0x00020002u;
-                const uint32_t la = (la4 >> (8 * k)) & 0xffu, lb = (lb4 >> (8 * k)) & 0xffu;
-                const uint32_t aA = sprofA + la * PS, aB = sprofB + lb * PS;
-                uint32_t pa[NPW], pb[NPW];
+                for (int w = 0; w < PQ; ++w) acc[w] = 0;
 #pragma unroll
-                for (int w = 0; w < NPW; ++w) { pa[w] = lds_u32(aA + 4 * w); pb[w] = lds_u32(aB + 4 * w); }
-                uint32_t bmax[nblk_for(R)];
-                sweep_column16<R, LOCAL, PQ>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * k, bmax);
-                cur.top[k] = top;
-                prevTop = top;
-                bottom = c[R - 1];
-                if (LOCAL) {
-                    uint32_t m = bmax[0];
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
+                    if (!LOCAL) border = __vsub2(border, G2);
+                    const uint32_t top = (l == 0) ? (LOCAL ? 0u : border) : up;
+                    const uint32_t KLk = (LOCAL || NKEEP * o + 4 * h + k >= l) ? KL2 : 0x00020002u;
+                    const uint32_t la = (la4 >> (8 * k)) & 0xffu, lb = (lb4 >> (8 * k)) & 0xffu;
+                    const uint32_t aA = sprofA + la * PS, aB = sprofB + lb * PS;
+                    uint32_t pa[NPW], pb[NPW];
 #pragma unroll
-                    for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
-                    cm[k] = m;
+                    for (int w = 0; w < NPW; ++w) { pa[w] = lds_u32(aA + 4 * w); pb[w] = lds_u32(aB + 4 * w); }
+                    uint32_t bmax[nblk_for(R)];
+                    sweep_column16<R, LOCAL, PQ>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * k, bmax);
+                    cur.top[4 * h + k] = top;
+                    prevTop = top;
+                    bottom = c[R - 1];
+                    if (LOCAL) {
+                        uint32_t m = bmax[0];
+#pragma unroll
+                        for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
+                        cm[4 * h + k] = m;
+                    }
                 }
-            }
-            // the quad's tags: one or two 128-bit stores per lane
-            if (PQ == 2) *reinterpret_cast<uint2 *>(dptr) = make_uint2(acc[0], acc[1]);
-            else {
+                // the quad's tags: one or two 128-bit stores per lane
+                if (PQ == 2) *reinterpret_cast<uint2 *>(dptr) = make_uint2(acc[0], acc[1]);
+                else {
 #pragma unroll
-                for (int w = 0; w < PQ; w += 4)
-                    *reinterpret_cast<uint4 *>(dptr + w) = make_uint4(acc[w], acc[w + 1 < PQ ? w + 1 : 0], acc[w + 2 < PQ ? w + 2 : 0], acc[w + 3 < PQ ? w + 3 : 0]);
+                    for (int w = 0; w < PQ; w += 4)
+                        *reinterpret_cast<uint4 *>(dptr + w) = make_uint4(acc[w], acc[w + 1 < PQ ? w + 1 : 0], acc[w + 2 < PQ ? w + 2 : 0], acc[w + 3 < PQ ? w + 3 : 0]);
+                }
+                dptr += 32 * PQ;
             }
-            dptr += 32 * PQ;
 
             if (!LOCAL) continue;        // global: the end cell is (m, n) and the traceback re-derives the score
-            // ---- arg-max bookkeeping, once per quad
-            const uint32_t qm = __vmaxs2(__vmaxs2(cm[0], cm[1]), __vmaxs2(cm[2], cm[3]));
+            // ---- arg-max bookkeeping, once per octet
+            uint32_t qm = cm[0];
+#pragma unroll
+            for (int k = 1; k < NKEEP; k += 2) qm = (k + 1 < NKEEP) ? __vimax3_s16x2(qm, cm[k], cm[k + 1 < NKEEP ? k + 1 : k]) : __vmaxs2(qm, cm[k]);
             const uint32_t nb = __vmaxs2(best2, qm);
             const uint32_t chg = nb ^ best2;
             const uint32_t eq = qm ^ best2;
@@ -342,28 +359,25 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
 #pragma unroll
             for (int r = 0; r < R; ++r) snap.c[r] = __byte_perm(snap.c[r], cur.c[r], sel);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) snap.top[k] = __byte_perm(snap.top[k], cur.top[k], sel);
+            for (int k = 0; k < NKEEP; ++k) snap.top[k] = __byte_perm(snap.top[k], cur.top[k], sel);
             snap.diag = __byte_perm(snap.diag, cur.diag, sel);
-            bestqA = impA ? q : bestqA;
-            bestqB = impB ? q : bestqB;
+            bestqA = impA ? o : bestqA;
+            bestqB = impB ? o : bestqB;
             best2 = nb;
             if (tieA || tieB) {
-                // the same maximum again in a later quad: it only replaces the kept one if it sits in a smaller row
-                const int aA_ = 4 * bestqA - l + TPAD, aB_ = 4 * bestqB - l + TPAD;
-                const uint32_t oa4 = __funnelshift_r(lds_u32(stextA + (aA_ & ~3)), lds_u32(stextA + (aA_ & ~3) + 4), 8 * (aA_ & 3));
-                const uint32_t ob4 = __funnelshift_r(lds_u32(stextB + (aB_ & ~3)), lds_u32(stextB + (aB_ & ~3) + 4), 8 * (aB_ & 3));
-                const uint32_t kOld = replay_quad16<R>(snap, best2, oa4, ob4, sprofA, sprofB, KL2, KT2);
-                const uint32_t kNew = replay_quad16<R>(cur, best2, la4, lb4, sprofA, sprofB, KL2, KT2);
-                const bool repA = tieA && ((kNew & 0xffffu) >> 2) < ((kOld & 0xffffu) >> 2);
-                const bool repB = tieB && ((kNew >> 16) >> 2) < ((kOld >> 16) >> 2);
+                // the same maximum again in a later octet: it only replaces the kept one if it sits in a smaller row
+                const uint32_t kOld = replay_quad16<R>(snap, best2, octet_letters(stextA, bestqA), octet_letters(stextB, bestqB), sprofA, sprofB, KL2, KT2);
+                const uint32_t kNew = replay_quad16<R>(cur, best2, octet_letters(stextA, o), octet_letters(stextB, o), sprofA, sprofB, KL2, KT2);
+                const bool repA = tieA && ((kNew & 0xffffu) / NKEEP) < ((kOld & 0xffffu) / NKEEP);
+                const bool repB = tieB && ((kNew >> 16) / NKEEP) < ((kOld >> 16) / NKEEP);
                 const uint32_t sel2 = (repA ? 0x54u : 0x10u) | (repB ? 0x7600u : 0x3200u);
 #pragma unroll
                 for (int r = 0; r < R; ++r) snap.c[r] = __byte_perm(snap.c[r], cur.c[r], sel2);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) snap.top[k] = __byte_perm(snap.top[k], cur.top[k], sel2);
+                for (int k = 0; k < NKEEP; ++k) snap.top[k] = __byte_perm(snap.top[k], cur.top[k], sel2);
                 snap.diag = __byte_perm(snap.diag, cur.diag, sel2);
-                bestqA = repA ? q : bestqA;
-                bestqB = repB ? q : bestqB;
+                bestqA = repA ? o : bestqA;
+                bestqB = repB ? o : bestqB;
             }
         }
 
@@ -373,15 +387,12 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
                 if (validB) { A.end_i[pairB] = mB; A.end_j[pairB] = nB; }
             }
         } else {
-            // ---- locate the first maximum inside each lane's kept quad, then reduce over the lanes
-            const int aA_ = 4 * bestqA - l + TPAD, aB_ = 4 * bestqB - l + TPAD;
-            const uint32_t oa4 = __funnelshift_r(lds_u32(stextA + (aA_ & ~3)), lds_u32(stextA + (aA_ & ~3) + 4), 8 * (aA_ & 3));
-            const uint32_t ob4 = __funnelshift_r(lds_u32(stextB + (aB_ & ~3)), lds_u32(stextB + (aB_ & ~3) + 4), 8 * (aB_ & 3));
-            const uint32_t key = replay_quad16<R>(snap, best2, oa4, ob4, sprofA, sprofB, KL2, KT2);
+            // ---- locate the first maximum inside each lane's kept octet, then reduce over the lanes
+            const uint32_t key = replay_quad16<R>(snap, best2, octet_letters(stextA, bestqA), octet_letters(stextB, bestqB), sprofA, sprofB, KL2, KT2);
             const int keyA = (int)(key & 0xffffu), keyB = (int)(key >> 16);
             int bestvA = half_of<0>(best2), bestvB = half_of<1>(best2);
-            int bestiA = l * R + (keyA >> 2) + 1, bestjA = 4 * bestqA + (keyA & 3) - l + 1;
-            int bestiB = l * R + (keyB >> 2) + 1, bestjB = 4 * bestqB + (keyB & 3) - l + 1;
+            int bestiA = l * R + keyA / NKEEP + 1, bestjA = NKEEP * bestqA + (keyA % NKEEP) - l + 1;
+            int bestiB = l * R + keyB / NKEEP + 1, bestjB = NKEEP * bestqB + (keyB % NKEEP) - l + 1;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
                 int ov = __shfl_xor_sync(0xffffffffu, bestvA, o), oi = __shfl_xor_sync(0xffffffffu, bestiA, o),

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
 #pragma unroll
             for (int r = 0; r < R; ++r) cur.c[r] = c[r];
             cur.diag = prevTop;
-            uint32_t cm[NKEEP];
+            uint32_t qm = 0u;                // maximum of the octet's cells: one VIMNMX3 chain through all eight columns
 #pragma unroll
             for (int h = 0; h < NKEEP / 4; ++h) {
                 pTextA += 4; pTextB += 4;
@@ -323,10 +323,9 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
                     prevTop = top;
                     bottom = c[R - 1];
                     if (LOCAL) {
-                        uint32_t m = bmax[0];
 #pragma unroll
-                        for (int b = 1; b < nblk_for(R); ++b) m = __vmaxs2(m, bmax[b]);
-                        cm[4 * h + k] = m;
+                        for (int r = 0; r + 1 < R; r += 2) qm = __vimax3_s16x2(qm, c[r], c[r + 1 < R ? r + 1 : r]);
+                        if (R & 1) qm = __vmaxs2(qm, c[R - 1]);
                     }
                 }
                 // the quad's tags: one or two 128-bit stores per lane
@@ -341,9 +340,6 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
 
             if (!LOCAL) continue;        // global: the end cell is (m, n) and the traceback re-derives the score
             // ---- arg-max bookkeeping, once per octet
-            uint32_t qm = cm[0];
-#pragma unroll
-            for (int k = 1; k < NKEEP; k += 2) qm = (k + 1 < NKEEP) ? __vimax3_s16x2(qm, cm[k], cm[k + 1 < NKEEP ? k + 1 : k]) : __vmaxs2(qm, cm[k]);
             const uint32_t nb = __vmaxs2(best2, qm);
             const uint32_t chg = nb ^ best2;
             const uint32_t eq = qm ^ best2;

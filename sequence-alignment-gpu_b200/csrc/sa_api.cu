@@ -1107,6 +1107,9 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
         A.top_row = c ? ckrow(c) : nullptr;
         A.bottom_row = (keepBottom && c + 1 < K) ? ckrow(c + 1) : nullptr;
         A.score = keepBottom ? d_score : d_scratch_score;
+        // pass 2: the path enters this chunk at column *d_col (left there by the traceback of the chunk below) and only
+        // moves left from there: the columns beyond are not filled again (1 000 000 x 950 793 in 3 chunks: 0.70 -> 0.57 s)
+        A.n_dev = (!keepBottom && P.C) ? d_col : nullptr;
         A.tag_base = (uint32_t)ctx->epoch << 21;
         A.gmax = reinterpret_cast<int *>(ctx->misc.as<char>() + 48);
         A.abort_flag = reinterpret_cast<int *>(ctx->misc.as<char>() + 56);

@@ -54,6 +54,9 @@ struct LongArgs {
     int *cand_v; uint32_t *cand_i; uint32_t *cand_j;   // SW: per-strip arg-max candidates
     uint32_t tag_base;       // per-call epoch << 21: ring entries of earlier calls never match
     int *gmax;               // SW: running alignment-wide maximum (4*H), zeroed per call
+    // Optional (tiled kernel): only the first *n_dev columns are filled (a device value, <= n).  The second pass of the
+    // checkpointed traceback needs a chunk only up to the column where the path entered it from below.
+    const int *n_dev;
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)

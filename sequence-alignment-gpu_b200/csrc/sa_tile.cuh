@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(WARPS * 32) tile_fill_kernel(const LongArgs A)
     static_assert(R <= SC || !LOCAL, "the arg-max key holds the lane's row in the free low bits");
     const int KL = 2 - SC * A.gap, KT = 1 - SC * A.gap;
     const uint32_t W = gridDim.x * WARPS;
-    const int n = (int)A.n, m = (int)A.m;
+    const int n = A.n_dev ? max(1, min((int)A.n, *A.n_dev)) : (int)A.n, m = (int)A.m;
     const int nTiles = (n + C - 1) / C;          // tiles per lane
     const int nFull = n / C;                     // tiles that lie completely inside the text
     const int kEnd = nTiles + 31;                // macro-steps of a strip

@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(128) tb_walkers_kernel(const TbArgs A)
     if (s == 0 || s > A.st->s0) return;          // lines above the start cell only
     const int q = tb_band_q0(A, s) + qi;
     if (q > A.Q) return;
-    const int c = min(q * A.Wd, A.Lay.n);
+    // (row chunk of a checkpointed traceback: the chunk is only filled up to the column where the path enters it)
+    const int c = min(q * A.Wd, A.start_col_dev ? A.st->j0 : A.Lay.n);
     A.fa[(size_t)s * nb + qi] = (uint32_t)tb_walk_to_row(A.Lay, s * A.Lay.ROWS, c, (s - 1) * A.Lay.ROWS, 3 * A.Lay.ROWS + 64);
 }
 
@@ -207,7 +208,7 @@ __global__ void tb_resolve_kernel(const TbArgs A)
         if (x == 0) nx = 0;
         else {
             const int q = x / A.Wd, q0 = tb_band_q0(A, s);
-            const int clo = min(q * A.Wd, A.Lay.n);
+            const int clo = min(q * A.Wd, A.start_col_dev ? A.st->j0 : A.Lay.n);
             const bool exact = clo == x;
             if (q < q0 || q + (exact ? 0 : 1) > min(q0 + 2 * A.BQ, A.Q)) {
                 nx = tb_walk_to_row(A.Lay, s * ROWS, x, (s - 1) * ROWS); ++fb;      // outside the band

@@ -779,13 +779,14 @@ struct LongPlan {
 // the delay per GPU of the linked slices of config 5.  Measured: a 125 000-column slice (3 716 strips) fills in 76.8 / 57.0 /
 // 63.5 / 72.6 ms with 1 / 2 / 3 / 4 blocks per SM and strip 0 crosses it in 9.5 / 11.8 / 13.7 / 14.8 ms; a 250 000-column
 // slice in 105 / 102 / 105 ms with 2 / 3 / 4, and config 5 on 4 GPUs in 0.199 / 0.218 / 0.236 s.  SA_LONG_BLOCKS_PER_SM overrides.
-// A fill whose strips all fit with three blocks per SM but not with two takes three (a second wave of a few strips costs a
-// whole sweep: 1 000 000 x 317 000, a chunk of the checkpointed traceback, 192 ms with two and 137 ms with three).
+// A fill whose strips all fit with three or four blocks per SM but not with two takes those (a second wave of a few
+// strips costs a whole sweep: 1 000 000 x 317 000, a chunk of the checkpointed traceback, 192 ms with two and 137 ms
+// with three).
 int tile_blocks_per_sm(const sa_context *ctx, uint64_t n_strips, int slices, int occ)
 {
     const uint64_t perBlockSm = (uint64_t)ctx->sms * TILE_WARPS;
     int perSm = 2;
-    if (slices <= 1 && n_strips > 2 * perBlockSm && n_strips <= 3 * perBlockSm) perSm = 3;
+    if (slices <= 1 && n_strips > 2 * perBlockSm && n_strips <= 4 * perBlockSm) perSm = n_strips <= 3 * perBlockSm ? 3 : 4;
     perSm = std::min(occ, perSm);
     if (const char *e = std::getenv("SA_LONG_BLOCKS_PER_SM")) { const int b = std::atoi(e); if (b >= 1) perSm = std::min(occ, b); }
     return perSm;
@@ -1154,7 +1155,7 @@ int enqueue_long_checkpointed(sa_context *ctx, const sa_scoring *sc, const uint8
 
 // When the packed directions of a GLOBAL alignment would not fit the device (or SA_CKPT_ROWS forces it), the pair takes the
 // checkpointed path.  SA_CKPT_LIMIT_MB: direction bytes above which it is taken (default 60 % of the device memory);
-// SA_CKPT_CHUNK_MB: direction bytes of one row chunk (default: half the device memory).
+// SA_CKPT_CHUNK_MB: direction bytes of one row chunk (default: 72 % of the device memory, 85 % of what is free).
 bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_t m, bool traceback, uint64_t *chunk_rows)
 {
     (void)traceback;                      // (a score-only call of that size runs the first pass alone)
@@ -1171,10 +1172,12 @@ bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_
     long double limit = 0.6L * (long double)totalB;
     if (const char *e = std::getenv("SA_CKPT_LIMIT_MB")) limit = (long double)std::atoll(e) * 1048576.0L;
     if (dirBytes <= limit) return false;
-    // chunks as tall as the memory allows, all of the same height: a chunk is one launch of the long-pair kernel, and a
-    // wide, low matrix keeps few strips busy (1 000 000 columns: 65 536 rows fill at 0.9 TCUPS, 390 000 rows at 2.7)
+    // chunks as tall as the memory allows, all of the same height: a chunk is one launch of the long-pair kernel, every
+    // launch pays one sweep of the text width whatever its height (1 000 000 columns: 65 536 rows fill at 0.9 TCUPS,
+    // 390 000 rows at 2.7), and the second pass re-fills all chunks but the last.  72 % of the device for one chunk's
+    // directions leaves room for the row ring (15 GB at 1 M columns) and the rest.
     // (what is free now plus what the context already holds for directions: other users of the device count)
-    long double chunkBytes = std::min(std::min(limit, 0.5L * (long double)totalB), 0.85L * ((long double)freeB + (long double)ctx->dirs.cap));
+    long double chunkBytes = std::min(0.72L * (long double)totalB, 0.85L * ((long double)freeB + (long double)ctx->dirs.cap));
     if (const char *e = std::getenv("SA_CKPT_CHUNK_MB")) chunkBytes = (long double)std::atoll(e) * 1048576.0L;
     const uint64_t rowsMax = std::max<uint64_t>(1024, (uint64_t)(chunkBytes * 4.0L / (long double)(n + 64)));
     const uint64_t K = (m + rowsMax - 1) / rowsMax;

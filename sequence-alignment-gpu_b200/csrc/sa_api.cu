@@ -132,7 +132,10 @@ struct sa_context {
     // bytes of direction workspace per chunk.  About 120 k pairs of 300 aa per chunk is the sweet spot on B200
     // (measured per 1 M pairs: 32.2 ms at 2 GB, 30.0 at 3 GB, 29.0 at 6 GB, 31.6 at 9 GB): the scattered tag reads of
     // the traceback start missing the TLB / L2 with larger chunks, smaller chunks pay more launches and tails.
-    size_t dirs_budget = (size_t)6 << 30;
+    size_t dirs_budget = (size_t)6 << 30;         // host-buffer batches: the eighths of the graded schedule must fit one set
+    // device-resident batches: chunks of ~80 000 pairs of config 4.  The traceback's scattered reads want the chunk's
+    // directions small (1 M pairs on B200: 3383 / 3435 / 3471 / 3489 GCUPS with 6 / 8 / 10 / 12 chunks)
+    size_t dev_dirs_budget = (size_t)3500 << 20;
     size_t host_dirs_budget = (size_t)8 << 30;    // host path: split over its NSLOT slots
     int tb_blocks_per_sm = 1;               // traceback blocks per SM while the next chunk's fill shares the GPU
 };
@@ -240,7 +243,7 @@ bool cfg_exists(int R, int L)
 
 size_t batch_task_stride(const BatchCfg &c, uint32_t max_n, int packed)
 {
-    if (packed == 2) return (((size_t)max_n + 31 + 7) / 8) * 2 * 32 * pq_for(c.R);   // quad layout (sa_batch16_sw.cuh), whole octets of columns
+    if (packed == 2) return (((size_t)max_n + 31 + 7) / 8) * 32 * po_for(c.R);       // octet layout (sa_batch16_sw.cuh), whole octets of columns
     const int CB = packed ? cb16_for(c.R) : cb_for(c.R), NW = c.R * CB / (packed ? 8 : 16);
     const size_t nblocks = ((size_t)max_n + c.L - 1 + CB - 1) / CB;
     return nblocks * NW * 32;
@@ -297,7 +300,7 @@ bool build_class_table(uint32_t max_n, uint32_t max_m, bool allow16, bool line, 
         if (T->n_classes == MAX_CLASSES) break;
         const int k = T->n_classes++;
         T->R[k] = c.R; T->L[k] = c.L; T->max_rows[k] = (uint32_t)(c.R * c.L);
-        // 2: straight-line kernel with the quad direction layout, 1: batch_fill16_kernel, 0: s32 kernel
+        // 2: straight-line kernel with the octet direction layout, 1: batch_fill16_kernel, 0: s32 kernel
         T->packed[k] = !allow16 ? 0 : (line && sw16_exists(c)) ? 2 : cfg16_exists(c.R, c.L) ? 1 : 0;
         T->stride[k] = batch_task_stride(c, max_n, T->packed[k]);
         if ((uint32_t)(c.R * c.L) >= max_m) break;      // larger classes cannot occur
@@ -1291,7 +1294,8 @@ int sa_create(int device, sa_context **out)
         cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.out, cudaEventDisableTiming);
     }
-    if (const char *e = std::getenv("SA_DIRS_BUDGET_MB")) ctx->dirs_budget = (size_t)std::atoll(e) << 20;
+    if (const char *e = std::getenv("SA_DIRS_BUDGET_MB")) ctx->dirs_budget = ctx->dev_dirs_budget = (size_t)std::atoll(e) << 20;
+    if (const char *e = std::getenv("SA_DEV_DIRS_BUDGET_MB")) ctx->dev_dirs_budget = (size_t)std::atoll(e) << 20;
     if (const char *e = std::getenv("SA_HOST_DIRS_BUDGET_MB")) ctx->host_dirs_budget = (size_t)std::atoll(e) << 20;
     // The small kernels that share the GPU with the fill must ask for the same (maximum) shared-memory carve-out:
     // an SM only changes its L1/shared split when it is empty, so with their default split the fill blocks of the
@@ -1774,7 +1778,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     // Chunks are software-pipelined: sort+fill of chunk c+1 runs on the caller's stream while the
     // (latency-bound) traceback of chunk c runs on the context's stream; two buffer sets.
     const double perPair = (double)batch_dirs_bound(T, 1 << 20) / (double)(1 << 20) * 4.0;      // bytes per pair
-    uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dirs_budget / perPair));
+    uint64_t chunk = std::max<uint64_t>(32, (uint64_t)((double)ctx->dev_dirs_budget / perPair));
     const char *ps = std::getenv("SA_BATCH_PIPELINE");
     const bool pipeline = !(ps && ps[0] == '0') && b->n_pairs >= 8192;
     // at least 4 chunks to overlap; small batches 2 -- every chunk costs ~0.15 ms of binning and kernel tails

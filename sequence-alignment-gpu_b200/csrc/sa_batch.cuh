@@ -33,7 +33,7 @@ struct BatchClassTable {            // static description, passed by value
     int n_classes;
     int R[MAX_CLASSES], L[MAX_CLASSES];
     int packed[MAX_CLASSES];        // 1: s16x2 kernel, two pairs per lane group (sa_batch16.cuh); 2: same, straight-line
-                                    //    kernel with the quad direction layout (sa_batch16_sw.cuh)
+                                    //    kernel with the octet direction layout (sa_batch16_sw.cuh)
     uint32_t max_rows[MAX_CLASSES];
     unsigned long long stride[MAX_CLASSES];     // direction words per task
     uint32_t max_text;              // pairs with a longer text are skipped (host aligns them one by one)
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
         int cls = 0;
         while (gpos >= A.dyn[cls].first + A.dyn[cls].count) ++cls;
         const int cR = A.table.R[cls], cL = A.table.L[cls];
-        const int layout = A.table.packed[cls];                  // 0: s32, 1: s16x2 warp-step-major, 2: s16x2 quad layout
+        const int layout = A.table.packed[cls];                  // 0: s32, 1: s16x2 warp-step-major, 2: s16x2 octet layout
         const bool packed = layout != 0;
         const int cCB = layout == 1 ? ((cR % 8 == 0) ? 1 : (cR % 4 == 0) ? 2 : 4) : cb_for(cR);
         const int G = 32 / cL;
@@ -363,11 +363,11 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
         // block kk, cell = kk*R + r; the word of a cell is kb*KBS + lane*LS + (cell >> cs)*CS (32-bit: a task has
         // fewer than 2^32 words).
         const int cs = packed ? 3 : 4;
-        const int kbShift = layout == 2 ? 2 : (cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3);
+        const int kbShift = layout == 2 ? 3 : (cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3);
         const int kkMask = (1 << kbShift) - 1;
-        const int PQ = (cR + 1) / 2 <= 2 ? 2 : (cR + 1) / 2 <= 4 ? 4 : 8;                 // pq_for(R)
-        const uint32_t KBS = layout == 2 ? 32u * PQ : (uint32_t)((cR * cCB) >> cs) * 32u;
-        const uint32_t LS = layout == 2 ? (uint32_t)PQ : 1u, CS = layout == 2 ? 1u : 32u;
+        const int PO = (cR + 1) & ~1;                                                     // po_for(R)
+        const uint32_t KBS = layout == 2 ? 32u * PO : (uint32_t)((cR * cCB) >> cs) * 32u;
+        const uint32_t LS = layout == 2 ? (uint32_t)PO : 1u, CS = layout == 2 ? 1u : 32u;
         const int cmask = (1 << cs) - 1;
 
         int i = (int)A.end_i[pair], j = (int)A.end_j[pair];

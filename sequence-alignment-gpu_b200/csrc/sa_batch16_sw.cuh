@@ -40,12 +40,13 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t saddr)
     return v;
 }
 
-// Direction words of the straight-line kernels ("quad layout", BatchClassTable.packed == 2): the tags of one lane
-// for FOUR columns (4*R cells x 2 pairs = ceil(R/2) words) are contiguous and padded to PQ = 2/4/8 words, a quad of a
-// warp is 32*PQ words:   word(task, q, lane, w) at task*stride + (q*32 + lane)*PQ + w,  cell = (k&3)*R + r.
-// A path that crosses a lane's rows then reads one or two 32-byte sectors per quad instead of a new 128-byte
-// line on almost every step (the warp-step-major layout), which is what bounds the batch traceback.
-__host__ __device__ constexpr int pq_for(int R) { return (R + 1) / 2 <= 2 ? 2 : (R + 1) / 2 <= 4 ? 4 : 8; }
+// Direction words of the straight-line kernels ("octet layout", BatchClassTable.packed == 2): the tags of one lane
+// for EIGHT columns (8*R cells x 2 pairs = R words) are contiguous, padded to PO = R rounded up to an even count, and an
+// octet of a warp is 32*PO words:   word(task, o, lane, w) at task*stride + (o*32 + lane)*PO + w,  cell = (k&7)*R + r.
+// A path that crosses a lane's rows then reads one or two 32-byte sectors per octet instead of a new 128-byte
+// line on almost every step (the warp-step-major layout), which is what bounds the batch traceback.  (Until round 2
+// the unit was a quad of four columns padded to 2/4/8 words: R = 9..12 stored 5-6 words as 8, 1.33-1.6 x the bytes.)
+__host__ __device__ constexpr int po_for(int R) { return (R + 1) & ~1; }
 
 constexpr int NKEEP = 8;         // columns per arg-max bookkeeping interval (two quads)
 template <int R>
@@ -182,8 +183,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 template <int R, bool LOCAL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArgs A)
 {
-    static_assert(R >= 2 && R <= 16, "4*R cells of a quad must fit PQ <= 8 words");
-    constexpr int PQ = pq_for(R);
+    static_assert(R >= 2 && R <= 16, "strip heights of the packed classes");
+    constexpr int PO = po_for(R);            // direction words per lane and octet
+    constexpr int SW = (PO % 4 == 0) ? 4 : 2; // words per store: 128-bit when the lane stride keeps them aligned
     constexpr int RPAD = rpad_for(R);
     constexpr int PS = 32 * RPAD;
     constexpr int NPW = (R + 3) / 4;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
         for (int k = 0; k < NKEEP; ++k) snap.top[k] = 0u;
         snap.diag = 0u;
 
-        uint32_t *dptr = dirs + (size_t)task * A.task_stride + lane * PQ;
+        uint32_t *dptr = dirs + (size_t)task * A.task_stride + lane * PO;
         uint32_t pTextA = stextA + 4 * word0, pTextB = stextB + 4 * word0;
         uint32_t wA0 = lds_u32(pTextA), wB0 = lds_u32(pTextB);
         // the eight letters of octet o for this lane (byte k = column 8*o + k)
@@ -297,29 +299,30 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
             for (int r = 0; r < R; ++r) cur.c[r] = c[r];
             cur.diag = prevTop;
             uint32_t qm = 0u;                // maximum of the octet's cells: one VIMNMX3 chain through all eight columns
+            uint32_t acc[PO];
+#pragma unroll
+            for (int w = 0; w < PO; ++w) acc[w] = 0;
 #pragma unroll
             for (int h = 0; h < NKEEP / 4; ++h) {
                 pTextA += 4; pTextB += 4;
                 const uint32_t wA1 = lds_u32(pTextA), wB1 = lds_u32(pTextB);
                 const uint32_t la4 = __funnelshift_r(wA0, wA1, 8 * phase), lb4 = __funnelshift_r(wB0, wB1, 8 * phase);
                 wA0 = wA1; wB0 = wB1;
-                uint32_t acc[PQ];
-#pragma unroll
-                for (int w = 0; w < PQ; ++w) acc[w] = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    const int kc = 4 * h + k;                  // column inside the octet
                     const uint32_t up = __shfl_up_sync(0xffffffffu, bottom, 1);
                     if (!LOCAL) border = __vsub2(border, G2);
                     const uint32_t top = (l == 0) ? (LOCAL ? 0u : border) : up;
-                    const uint32_t KLk = (LOCAL || NKEEP * o + 4 * h + k >= l) ? KL2 : 0x00020002u;
+                    const uint32_t KLk = (LOCAL || NKEEP * o + kc >= l) ? KL2 : 0x00020002u;
                     const uint32_t la = (la4 >> (8 * k)) & 0xffu, lb = (lb4 >> (8 * k)) & 0xffu;
                     const uint32_t aA = sprofA + la * PS, aB = sprofB + lb * PS;
                     uint32_t pa[NPW], pb[NPW];
 #pragma unroll
                     for (int w = 0; w < NPW; ++w) { pa[w] = lds_u32(aA + 4 * w); pb[w] = lds_u32(aB + 4 * w); }
                     uint32_t bmax[nblk_for(R)];
-                    sweep_column16<R, LOCAL, PQ>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * k, bmax);
-                    cur.top[4 * h + k] = top;
+                    sweep_column16<R, LOCAL, PO>(c, top, prevTop, pa, pb, KLk, KT2, acc, R * kc, bmax);
+                    cur.top[kc] = top;
                     prevTop = top;
                     bottom = c[R - 1];
                     if (LOCAL) {
@@ -327,16 +330,19 @@ __global__ void __launch_bounds__(WARPS * 32) batch_line16_kernel(const BatchArg
                         for (int r = 0; r + 1 < R; r += 2) qm = __vimax3_s16x2(qm, c[r], c[r + 1 < R ? r + 1 : r]);
                         if (R & 1) qm = __vmaxs2(qm, c[R - 1]);
                     }
-                }
-                // the quad's tags: one or two 128-bit stores per lane
-                if (PQ == 2) *reinterpret_cast<uint2 *>(dptr) = make_uint2(acc[0], acc[1]);
-                else {
+                    // the octet's tags go out as soon as a store's worth of words is complete (word w holds cells
+                    // 8w .. 8w+7): few accumulators are alive at a time
 #pragma unroll
-                    for (int w = 0; w < PQ; w += 4)
-                        *reinterpret_cast<uint4 *>(dptr + w) = make_uint4(acc[w], acc[w + 1 < PQ ? w + 1 : 0], acc[w + 2 < PQ ? w + 2 : 0], acc[w + 3 < PQ ? w + 3 : 0]);
+                    for (int w = 0; w < PO; w += SW) {
+                        const int lastCell = (8 * (w + SW) - 1 < 8 * R - 1) ? 8 * (w + SW) - 1 : 8 * R - 1;
+                        if (lastCell / R == kc) {
+                            if (SW == 4) *reinterpret_cast<uint4 *>(dptr + w) = make_uint4(acc[w], acc[w + 1], acc[w + 2], acc[w + 3]);
+                            else *reinterpret_cast<uint2 *>(dptr + w) = make_uint2(acc[w], acc[w + 1]);
+                        }
+                    }
                 }
-                dptr += 32 * PQ;
             }
+            dptr += 32 * PO;
 
             if (!LOCAL) continue;        // global: the end cell is (m, n) and the traceback re-derives the score
             // ---- arg-max bookkeeping, once per octet

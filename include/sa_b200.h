@@ -95,6 +95,15 @@ int sa_device_count(void);
  * call like initMemory does (alignSequenceGPU.cu:362-461). */
 int sa_create(int device, sa_context **out);
 void sa_destroy(sa_context *ctx);
+/* Tuning knobs of a context by name (the reference has none: its launch shape is compiled in, alignSequenceGPU.cu:7-12).
+ * Sizes in MB.  "dev_dirs_budget_mb" / "dirs_budget_mb" / "host_dirs_budget_mb": direction words per chunk of the
+ * device-resident batch / of the staged host batch / of the slot pipeline; "batch_min_chunks": floor of the chunk count
+ * of a device batch (0 = automatic); "tb_blocks_per_sm": traceback blocks next to the following chunk's fill;
+ * "ckpt_rows" / "ckpt_limit_mb" / "ckpt_chunk_mb": checkpointed traceback of global alignments -- rows per chunk,
+ * direction bytes above which it is taken, direction bytes of one chunk (0 = automatic).  Unknown names and values
+ * out of range return SA_ERR_ARGUMENT.  The SA_* environment variables remain as developer overrides. */
+int sa_set_option(sa_context *ctx, const char *name, long long value);
+int sa_get_option(const sa_context *ctx, const char *name, long long *value);
 
 const char *sa_status_string(int status);
 int sa_last_timing(const sa_context *ctx, sa_timing *out);

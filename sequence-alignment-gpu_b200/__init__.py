@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
         L.sa_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.sa_destroy.argtypes = [C.c_void_p]
         L.sa_last_timing.argtypes = [C.c_void_p, C.POINTER(_Timing)]
+        L.sa_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+        L.sa_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_longlong)]
         L.sa_last_cuda_error.argtypes = [C.c_void_p]
         L.sa_context_stream.restype = C.c_void_p
         L.sa_context_stream.argtypes = [C.c_void_p]
@@ -219,6 +221,15 @@ class Aligner:
         if rc != 0:
             raise SaError(rc, self._L.sa_status_string(rc).decode() +
                           f" (cuda error {self._L.sa_last_cuda_error(self._ctx)})")
+
+    def set_option(self, name: str, value: int):
+        """Tuning knob of this context (sa_set_option): e.g. dev_dirs_budget_mb, batch_min_chunks, ckpt_rows."""
+        self._check(self._L.sa_set_option(self._ctx, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_longlong()
+        self._check(self._L.sa_get_option(self._ctx, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def timing(self) -> dict:
         t = _Timing()

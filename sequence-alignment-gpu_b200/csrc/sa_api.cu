@@ -138,6 +138,8 @@ struct sa_context {
     size_t dev_dirs_budget = (size_t)3500 << 20;
     size_t host_dirs_budget = (size_t)8 << 30;    // host path: split over its NSLOT slots
     int tb_blocks_per_sm = 1;               // traceback blocks per SM while the next chunk's fill shares the GPU
+    // sa_set_option (0 = automatic): chunk count floor of the device batch, checkpointed traceback of global alignments
+    long long batch_min_chunks = 0, ckpt_rows = 0, ckpt_limit_mb = 0, ckpt_chunk_mb = 0;
 };
 
 namespace {
@@ -1163,17 +1165,20 @@ bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_
 {
     (void)traceback;                      // (a score-only call of that size runs the first pass alone)
     if (sc->mode != SA_GLOBAL || ctx->wide) return false;
-    if (const char *e = std::getenv("SA_CKPT_ROWS")) {
-        const long long r = std::atoll(e);
+    const char *eRows = std::getenv("SA_CKPT_ROWS");
+    if (eRows || ctx->ckpt_rows > 0) {
+        const long long r = eRows ? std::atoll(eRows) : ctx->ckpt_rows;
         if (r > 0 && (uint64_t)r < m) { *chunk_rows = (uint64_t)r; return true; }
         return false;
     }
+    const char *eLimit = std::getenv("SA_CKPT_LIMIT_MB");
     const long double dirBytes = (long double)(n + 64) * (long double)(m + 512) / 4.0L;
-    if (dirBytes < 4.0L * 1073741824.0L && !std::getenv("SA_CKPT_LIMIT_MB")) return false;      // (cudaMemGetInfo costs milliseconds)
+    if (dirBytes < 4.0L * 1073741824.0L && !eLimit && ctx->ckpt_limit_mb <= 0) return false;      // (cudaMemGetInfo costs milliseconds)
     size_t freeB = 0, totalB = 0;
     if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) { cudaGetLastError(); return false; }
     long double limit = 0.6L * (long double)totalB;
-    if (const char *e = std::getenv("SA_CKPT_LIMIT_MB")) limit = (long double)std::atoll(e) * 1048576.0L;
+    if (ctx->ckpt_limit_mb > 0) limit = (long double)ctx->ckpt_limit_mb * 1048576.0L;
+    if (eLimit) limit = (long double)std::atoll(eLimit) * 1048576.0L;
     if (dirBytes <= limit) return false;
     // chunks as tall as the memory allows, all of the same height: a chunk is one launch of the long-pair kernel, every
     // launch pays one sweep of the text width whatever its height (1 000 000 columns: 65 536 rows fill at 0.9 TCUPS,
@@ -1181,6 +1186,7 @@ bool want_checkpoints(sa_context *ctx, const sa_scoring *sc, uint64_t n, uint64_
     // directions leaves room for the row ring (15 GB at 1 M columns) and the rest.
     // (what is free now plus what the context already holds for directions: other users of the device count)
     long double chunkBytes = std::min(0.72L * (long double)totalB, 0.85L * ((long double)freeB + (long double)ctx->dirs.cap));
+    if (ctx->ckpt_chunk_mb > 0) chunkBytes = (long double)ctx->ckpt_chunk_mb * 1048576.0L;
     if (const char *e = std::getenv("SA_CKPT_CHUNK_MB")) chunkBytes = (long double)std::atoll(e) * 1048576.0L;
     const uint64_t rowsMax = std::max<uint64_t>(1024, (uint64_t)(chunkBytes * 4.0L / (long double)(n + 64)));
     const uint64_t K = (m + rowsMax - 1) / rowsMax;
@@ -1310,6 +1316,54 @@ int sa_create(int device, sa_context **out)
     if (const char *e = std::getenv("SA_TB_BLOCKS_PER_SM")) ctx->tb_blocks_per_sm = std::max(1, std::atoi(e));
     *out = ctx;
     return SA_OK;
+}
+
+// Tuning knobs of a context by name (the SA_* environment variables of the same names are developer overrides read
+// when the context is created or per call).  Sizes in MB; 0 restores the automatic choice where there is one.
+namespace {
+struct OptRef { const char *name; int kind; };      // kind 0: size_t bytes given in MB, 1: long long, 2: int >= 1
+long long *opt_ll(sa_context *c, const char *n)
+{
+    if (!std::strcmp(n, "batch_min_chunks")) return &c->batch_min_chunks;
+    if (!std::strcmp(n, "ckpt_rows")) return &c->ckpt_rows;
+    if (!std::strcmp(n, "ckpt_limit_mb")) return &c->ckpt_limit_mb;
+    if (!std::strcmp(n, "ckpt_chunk_mb")) return &c->ckpt_chunk_mb;
+    return nullptr;
+}
+size_t *opt_mb(sa_context *c, const char *n)
+{
+    if (!std::strcmp(n, "dirs_budget_mb")) return &c->dirs_budget;
+    if (!std::strcmp(n, "dev_dirs_budget_mb")) return &c->dev_dirs_budget;
+    if (!std::strcmp(n, "host_dirs_budget_mb")) return &c->host_dirs_budget;
+    return nullptr;
+}
+} // namespace
+
+int sa_set_option(sa_context *ctx, const char *name, long long value)
+{
+    if (!ctx || !name || value < 0) return SA_ERR_ARGUMENT;
+    if (size_t *p = opt_mb(ctx, name)) {
+        if (value < 1) return SA_ERR_ARGUMENT;
+        *p = (size_t)value << 20;
+        return SA_OK;
+    }
+    if (long long *p = opt_ll(ctx, name)) { *p = value; return SA_OK; }
+    if (!std::strcmp(name, "tb_blocks_per_sm")) {
+        if (value < 1 || value > 16) return SA_ERR_ARGUMENT;
+        ctx->tb_blocks_per_sm = (int)value;
+        return SA_OK;
+    }
+    return SA_ERR_ARGUMENT;
+}
+
+int sa_get_option(const sa_context *ctx, const char *name, long long *value)
+{
+    if (!ctx || !name || !value) return SA_ERR_ARGUMENT;
+    sa_context *c = const_cast<sa_context *>(ctx);
+    if (const size_t *p = opt_mb(c, name)) { *value = (long long)(*p >> 20); return SA_OK; }
+    if (const long long *p = opt_ll(c, name)) { *value = *p; return SA_OK; }
+    if (!std::strcmp(name, "tb_blocks_per_sm")) { *value = ctx->tb_blocks_per_sm; return SA_OK; }
+    return SA_ERR_ARGUMENT;
 }
 
 void sa_destroy(sa_context *ctx)
@@ -1784,6 +1838,7 @@ int sa_align_batch_device(sa_context *ctx, const sa_scoring *sc, const sa_batch 
     // at least 4 chunks to overlap; small batches 2 -- every chunk costs ~0.15 ms of binning and kernel tails
     // (125 000 pairs: 3.51 / 3.55 / 3.62 / 3.79 ms with 2 / 3 / 4 / 6 chunks; 250 000: 7.18 / 6.96 / 6.85 / 6.86)
     uint64_t minChunks = b->n_pairs >= 200000 ? 4 : 2;
+    if (ctx->batch_min_chunks >= 1) minChunks = (uint64_t)ctx->batch_min_chunks;
     if (const char *e = std::getenv("SA_BATCH_MIN_CHUNKS")) { const int v = std::atoi(e); if (v >= 1) minChunks = (uint64_t)v; }
     if (pipeline) chunk = std::min<uint64_t>(chunk, (b->n_pairs + minChunks - 1) / minChunks);
     chunk = std::min<uint64_t>(chunk, b->n_pairs);

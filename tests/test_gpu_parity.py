@@ -621,6 +621,42 @@ def test_host_batch_csr_with_nonzero_first_offset(sa, aligner, oracle, monkeypat
     assert N == len(out["results"])
 
 
+def test_context_options_replace_the_environment(sa, oracle):
+    """sa_set_option / sa_get_option: the chunking of the device batch set through the C ABI instead of SA_* variables
+    (eight or more chunks of a 12 000-pair batch), results equal to the oracle's; unknown names and bad values refused."""
+    import synth
+    al = sa.Aligner(0)
+    try:
+        assert al.get_option("dev_dirs_budget_mb") == 3500
+        al.set_option("dev_dirs_budget_mb", 64)
+        al.set_option("tb_blocks_per_sm", 2)
+        assert al.get_option("dev_dirs_budget_mb") == 64 and al.get_option("tb_blocks_per_sm") == 2
+        for bad in (("no_such_option", 1), ("dev_dirs_budget_mb", 0), ("tb_blocks_per_sm", 99), ("ckpt_rows", -1)):
+            with pytest.raises(sa.SaError):
+                al.set_option(*bad)
+        with pytest.raises(sa.SaError):
+            al.get_option("no_such_option")
+        T, toff, P, poff = synth.synthetic_batch(12000, seed=99)
+        mat = helpers.matrices()["protein/blosum62.txt"]
+        out = _device_batch(sa, al, 1, mat, T, toff, P, poff)
+        launches = al.timing()["kernel_launches"]
+        assert launches >= 8 * 5, launches
+        assert oracle.check_batch(1, 23, mat, 5, T, toff, P, poff, out) == (0, -1)
+        # the checkpointed traceback by option: a 3000 x 2800 global alignment in chunks of 700 rows
+        rng = np.random.default_rng(5)
+        t = rng.integers(0, 4, 3000, dtype=np.uint8)
+        p2 = t[:2800].copy(); p2[::17] = (p2[::17] + 1) % 4
+        dna = helpers.matrices()["dna/blast.txt"]
+        want = oracle.align(0, 4, dna, 5, t, p2)
+        al.set_option("ckpt_rows", 700)
+        got = al.align(0, 4, dna, 5, t, p2)
+        assert got.key() == want.key()
+        al.set_option("ckpt_rows", 0)
+        assert al.align(0, 4, dna, 5, t, p2).key() == want.key()
+    finally:
+        al.close()
+
+
 def test_residues_outside_the_alphabet_are_refused(sa, aligner):
     """include/sa_b200.h: a residue >= alphabet_size is SA_ERR_ARGUMENT from the host-buffer entry points."""
     import synth

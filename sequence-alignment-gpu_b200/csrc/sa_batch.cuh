@@ -327,6 +327,55 @@ struct BatchTraceArgs {
     uint32_t *stats;
 };
 
+// shared-memory bytes by 32-bit shared address (the generic form re-derives the shared window in every iteration)
+__device__ __forceinline__ uint32_t tb_lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int tb_lds_s8(uint32_t a) { int v; asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+// Residues read at a moving index, an aligned word at a time: the byte comes out with one PRMT.
+struct TbWordReader {
+    const uint32_t *base; int off; int curw; uint32_t w;
+    __device__ TbWordReader(const uint8_t *p) : base(reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3)),
+                                                 off((int)(reinterpret_cast<uintptr_t>(p) & 3)), curw(-1), w(0) {}
+    __device__ __forceinline__ int get(const int q) {
+        const int a = q + off, wi = a >> 2;
+        if (wi != curw) { curw = wi; w = __ldg(base + wi); }
+        return (int)__byte_perm(w, 0u, 0x4440u | (uint32_t)(a & 3));
+    }
+};
+
+// Characters written BACKWARDS from `end`, four at a time and at the same steps in every lane of the warp (the lanes
+// walk in lock-step, so `if ((len & 3) == 0)` is a uniform branch and the store code is issued on every fourth step
+// only).  `end` has any alignment a = end & 3: the group of four newest characters lies at end - len (address & 3 == a),
+// the aligned word stored at a flush is made of the older a characters of this group and the newest 4 - a of the one
+// before (a funnel shift); the a bytes right below `end` go out as bytes at the first flush, and finish() writes what
+// is still pending (the low 4 - a bytes of the last group -- all four when a = 0 -- and the len & 3 characters after the
+// last flush).
+struct TbBackWriter {
+    char *end; uint32_t a, cur, prev;
+    __device__ TbBackWriter(char *e) : end(e), a((uint32_t)(reinterpret_cast<uintptr_t>(e) & 3)), cur(0u), prev(0u) {}
+    __device__ __forceinline__ void push(const uint32_t c) { cur = (cur << 8) | c; }       // byte 0 = newest = lowest address
+    // len = 4, 8, ...: the same path in every lane (an aligned `end` is handled as a = 0 with the word one group late:
+    // the clamped funnel shift by 32 bits returns the group before, so no lane takes a branch of its own)
+    __device__ __forceinline__ void flush(const uint32_t len) {
+        char *q = end - len;
+        if (len == 4u) {
+#pragma unroll
+            for (uint32_t b = 1; b < 4u; ++b) if (b >= 4u - a) q[b] = (char)(cur >> (8u * b));
+        } else *reinterpret_cast<uint32_t *>(q + (4u - a)) = __funnelshift_rc(cur, prev, 8u * (4u - a));
+        prev = cur;
+    }
+    __device__ __forceinline__ void finish(const uint32_t len) {
+        const uint32_t rem = len & 3u, full = len - rem;
+        if (full >= 4u) {                  // the low 4 - a bytes of the last group
+            char *q = end - full;
+            if (a == 0u) *reinterpret_cast<uint32_t *>(q) = prev;
+            else for (uint32_t b = 0; b < 4u - a; ++b) q[b] = (char)(prev >> (8u * b));
+        }
+        char *q = end - len;
+        for (uint32_t b = 0; b < rem; ++b) q[b] = (char)(cur >> (8u * b));
+    }
+};
+
 __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceArgs A)
 {
     // Alphabet (+ gap character at index alpha) and the score matrix as bytes in shared memory: per-lane indices
@@ -338,6 +387,8 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
     for (int i = threadIdx.x; i < A.alpha * A.alpha; i += blockDim.x) S8[i] = (signed char)A.S[i];      // |S| <= 31 (upload_scoring)
     __syncthreads();
     const int alpha = A.alpha, gap = A.gap;
+    uint32_t sAlph = (uint32_t)__cvta_generic_to_shared(alphS), sS8 = (uint32_t)__cvta_generic_to_shared(S8);
+    asm volatile("" : "+r"(sAlph), "+r"(sS8));        // kept in registers: the compiler would re-derive the shared window per step
     // grid-stride over the pairs: a pipelined chunk launches only a few blocks per SM so that the fill blocks of the
     // next chunk fit next to them (a full grid would hold every SM until the traceback drains)
     for (uint32_t gpos = blockIdx.x * blockDim.x + threadIdx.x; gpos < A.dyn[A.table.n_classes].first; gpos += gridDim.x * blockDim.x) {
@@ -360,14 +411,15 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
         const uint64_t slotEnd = (uint64_t)(t0 + p0) + (uint64_t)(n + m);
 
         // One formula for the three direction layouts: step k = column-1 + lane, block kb = k >> kbShift, step in
-        // block kk, cell = kk*R + r; the word of a cell is kb*KBS + lane*LS + (cell >> cs)*CS (32-bit: a task has
+        // block kk, cell = kk*R + r; the word of a cell is kb*KBS + lane*LS + (cell >> cs) << csh (32-bit: a task has
         // fewer than 2^32 words).
         const int cs = packed ? 3 : 4;
         const int kbShift = layout == 2 ? 3 : (cCB == 1 ? 0 : cCB == 2 ? 1 : cCB == 4 ? 2 : 3);
         const int kkMask = (1 << kbShift) - 1;
         const int PO = (cR + 1) & ~1;                                                     // po_for(R)
         const uint32_t KBS = layout == 2 ? 32u * PO : (uint32_t)((cR * cCB) >> cs) * 32u;
-        const uint32_t LS = layout == 2 ? (uint32_t)PO : 1u, CS = layout == 2 ? 1u : 32u;
+        const uint32_t LS = layout == 2 ? (uint32_t)PO : 1u;
+        const int csh = layout == 2 ? 0 : 5;
         const int cmask = (1 << cs) - 1;
 
         int i = (int)A.end_i[pair], j = (int)A.end_j[pair];
@@ -376,45 +428,22 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
         uint32_t cachedIdx = ~0u, cachedWord = 0;
         // (lane, row-in-lane) of DP row i, kept incrementally: no integer division in the walk
         int ll = i > 0 ? (i - 1) / cR : 0, r = i > 0 ? (i - 1) % cR : 0;
+        uint32_t llLS = (uint32_t)ll * LS;
         auto fetch = [&](const int jj) -> int {
             const int k = (jj - 1) + ll;
             const int cell = (k & kkMask) * cR + r;
-            const uint32_t idx = (uint32_t)(k >> kbShift) * KBS + (uint32_t)ll * LS + (uint32_t)(cell >> cs) * CS;
-            if (idx != cachedIdx) { cachedIdx = idx; cachedWord = dbase[idx]; }
+            const uint32_t idx = (uint32_t)(k >> kbShift) * KBS + llLS + ((uint32_t)(cell >> cs) << csh);
+            if (idx != cachedIdx) { cachedIdx = idx; cachedWord = __ldg(dbase + idx); }
             return (cachedWord >> (2 * (cell & cmask) + halfBit)) & 3;
         };
-        auto row_up = [&]() { --i; if (r == 0) { r = cR - 1; --ll; } else --r; };
+        auto row_up = [&]() { --i; if (r == 0) { r = cR - 1; --ll; llLS -= LS; } else --r; };
 
-        // Residues are read an aligned word at a time and kept in registers; output characters are packed and
-        // stored an aligned word at a time (every lane walks its own pair: sector traffic is what counts).
-        struct WordReader {
-            const uint32_t *base; int off; int curw; uint32_t w;
-            __device__ WordReader(const uint8_t *p) : base(reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3)),
-                                                       off((int)(reinterpret_cast<uintptr_t>(p) & 3)), curw(-1), w(0) {}
-            __device__ __forceinline__ int get(const int q) {
-                const int a = q + off, wi = a >> 2;
-                if (wi != curw) { curw = wi; w = base[wi]; }
-                return (int)((w >> ((a & 3) * 8)) & 0xffu);
-            }
-        };
-        WordReader rdT(tx), rdP(pt);
-
-        // backwards writer: the next byte goes to p-1.  Up to three single bytes until the addresses are word
-        // aligned, then whole words (both strings share the alignment, or bytes only)
-        char *pT = A.out_text + slotEnd, *pP = A.out_pattern + slotEnd;
-        const bool wordOK = ((reinterpret_cast<uintptr_t>(pT) ^ reinterpret_cast<uintptr_t>(pP)) & 3) == 0;
-        int head = wordOK ? (int)(reinterpret_cast<uintptr_t>(pT) & 3) : 0x7fffffff;
-        uint32_t accT = 0, accP = 0; int cnt = 0;
+        TbWordReader rdT(tx), rdP(pt);
+        TbBackWriter wT(A.out_text + slotEnd), wP(A.out_pattern + slotEnd);
         auto emit = [&](const uint32_t cT, const uint32_t cP) {
-            if (head > 0) { *--pT = (char)cT; *--pP = (char)cP; --head; return; }
-            accT = (accT << 8) | cT;                  // little-endian: the lowest address ends up in bits 7:0
-            accP = (accP << 8) | cP;
-            if (++cnt == 4) {
-                pT -= 4; pP -= 4;
-                *reinterpret_cast<uint32_t *>(pT) = accT;
-                *reinterpret_cast<uint32_t *>(pP) = accP;
-                cnt = 0;
-            }
+            wT.push(cT); wP.push(cP);
+            ++len;
+            if ((len & 3u) == 0u) { wT.flush(len); wP.flush(len); }
         };
 
         int ti, pi;
@@ -426,10 +455,9 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
                 else if (i == 0) tag = TAG_LEFT;       // :80-81
                 else tag = fetch(j);
                 const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
-                ++len;
                 const int ct = rdT.get(ti), cp = rdP.get(pi);
-                emit(alphS[takeT ? ct : alpha], alphS[takeP ? cp : alpha]);
-                H += (tag == TAG_DIAG) ? (int)S8[cp * alpha + ct] : -gap;      // the path's score is H(m, n)
+                emit(tb_lds_u8(sAlph + (takeT ? ct : alpha)), tb_lds_u8(sAlph + (takeP ? cp : alpha)));
+                H += (tag == TAG_DIAG) ? tb_lds_s8(sS8 + cp * alpha + ct) : -gap;      // the path's score is H(m, n)
                 nDiag += (tag == TAG_DIAG); nIdent += (tag == TAG_DIAG && ct == cp);
                 ti = max(0, ti - (int)takeT);
                 pi = max(0, pi - (int)takeP);
@@ -437,26 +465,24 @@ __global__ void __launch_bounds__(256) batch_traceback_kernel(const BatchTraceAr
                 j -= takeT;
             }
         } else {
-            ti = j - 1; pi = i - 1;                    // :13-14 (-1/-1 when the best score is 0)
+            // :13-14: ti = j-1, pi = i-1 (-1/-1 when the best score is 0).  Inside the matrix the clamped indices of the
+            // reference stay at j-1 / i-1, so they are not carried: the residues are read at j-1 / i-1, and the break before
+            // the index update (:45-46) leaves them one step behind in the direction(s) taken last (adjT / adjP).
+            int adjT = 0, adjP = 0;
             while (H > 0) {                            // H(i,j) == 0  <=>  reference STOP
                 const int tag = fetch(j);
                 const bool takeT = tag != TAG_TOP, takeP = tag != TAG_LEFT;
-                ++len;
-                const int ct = rdT.get(ti), cp = rdP.get(pi);      // ti == j-1 and pi == i-1 inside the matrix
-                emit(alphS[takeT ? ct : alpha], alphS[takeP ? cp : alpha]);
-                H += (tag == TAG_DIAG) ? -(int)S8[cp * alpha + ct] : gap;
+                const int ct = rdT.get(j - 1), cp = rdP.get(i - 1);
+                emit(tb_lds_u8(sAlph + (takeT ? ct : alpha)), tb_lds_u8(sAlph + (takeP ? cp : alpha)));
+                H += (tag == TAG_DIAG) ? -tb_lds_s8(sS8 + cp * alpha + ct) : gap;
                 nDiag += (tag == TAG_DIAG); nIdent += (tag == TAG_DIAG && ct == cp);
                 if (takeP) row_up();
                 j -= takeT;
-                if (i == 0 || j == 0) break;           // :45-46, before the index update
-                ti = max(0, ti - (int)takeT);
-                pi = max(0, pi - (int)takeP);
+                if (i == 0 || j == 0) { adjT = (int)takeT; adjP = (int)takeP; break; }
             }
+            ti = j - 1 + adjT; pi = i - 1 + adjP;
         }
-        for (int q = cnt - 1; q >= 0; --q) {           // the characters still in the accumulators, oldest first
-            *--pT = (char)((accT >> (8 * q)) & 0xffu);
-            *--pP = (char)((accP >> (8 * q)) & 0xffu);
-        }
+        wT.finish(len); wP.finish(len);
         sa_result res;
         res.score = A.local ? A.score[pair] : H;
         res.aln_len = len;
